@@ -1,0 +1,459 @@
+"""ShufflingDataset: the per-epoch shuffling iterator (components C8, C9).
+
+Constructor signature, ``set_epoch`` contract (mandatory, must change every
+epoch, ``ValueError`` otherwise), "shuffling starts at construction for the
+first ``max_concurrent_epochs`` epochs", exact-``batch_size`` re-batching with
+an optional short tail (``drop_last``) and the ``task_done`` accounting are the
+reference's (``ray_shuffling_data_loader/dataset.py:15-205``).
+
+Architecture differences:
+
+* ranks are symmetric. In distributed mode (``torch.distributed`` initialised,
+  world size == ``num_trainers``) every process is mapper + reducer + trainer:
+  it runs its own shuffle-driver thread (the analogue of the reference's
+  ``ray.remote(shuffle)`` task, ``dataset.py:68-74``) and its own queue; there
+  is no rank-0 master to outlive the others (reference example sleeps 10 s for
+  that, ``ray_torch_shuffle.py:248-253``). In single-process mode rank 0 hosts
+  the engine for all trainers and other ranks connect to the named queue.
+* reducer outputs are row ranges of one contiguous epoch buffer, so re-batching
+  is pointer arithmetic (zero-copy views), and the reference's row-dropping
+  re-batcher bug (``dataset.py:160-168``) cannot occur: every row is
+  delivered exactly once per epoch.
+* in GPU mode batches are born in HBM; the iterator yields ``DeviceBatch``
+  (or pandas on the CPU backend, like the reference).
+* ``state_dict``/``load_state_dict`` give mid-epoch resume (the reference has no
+  checkpointing): the permutation is a pure function of
+  ``(seed, epoch)``.
+"""
+from __future__ import annotations
+
+import os
+import threading
+from typing import List, Optional
+
+from ray_shuffling_data_loader_b200.batch_queue import BatchQueue
+from ray_shuffling_data_loader_b200.parallel import bootstrap
+from ray_shuffling_data_loader_b200.runtime.chunks import (DeviceBatch,
+                                                           ShuffledChunk,
+                                                           packed_to_dataframe,
+                                                           _to_numpy)
+from ray_shuffling_data_loader_b200.shuffle import BatchConsumer, shuffle
+
+BATCHQUEUE_ACTOR_NAME = "BatchQueue"
+REDUCER_CLUSTER_CORE_SHARE = 0.6
+
+
+def get_num_cpus() -> int:
+    return os.cpu_count() or 1
+
+
+class ShufflingDataset:
+    """
+    A shuffling dataset that yields batches upon iteration.
+
+    This dataset will kick off shuffling for max_concurrent_epochs epochs at
+    construction time.
+
+    Args:
+        filenames (str): Paths to input Parquet files.
+        num_epochs (int): Number of training epochs.
+        num_trainers (int): Number of trainer workers.
+        batch_size (int): Size of the batches that the iterator should yield.
+        rank (int): The worker rank of the current process.
+        drop_last (Optional[bool]): Whether to drop the last batch if it's
+            incomplete (smaller than batch_size). Default is False.
+        num_reducers (Optional[int]): The number of shuffler reducers. Default
+            is the number of trainers x the number of cores x 0.6.
+        max_concurrent_epochs (Optional[int]): The maximum number of epochs
+            whose shuffling stages should execute concurrently. Default is 2.
+        seed (Optional[int]): permutation seed (``None``: random, agreed
+            across ranks). Same seed => same batches, on CPU and GPU.
+        backend: ``"cuda"``, ``"cpu"`` or ``None`` (auto).
+        output: ``"pandas"`` (CPU default), ``"device"`` (GPU default,
+            ``DeviceBatch``) or ``"packed"`` (raw ``uint8[B, pitch]``).
+        layout_fn: ``schema -> RowLayout`` (column projection + casts).
+        start_epoch: first epoch to shuffle (resume).
+    """
+
+    def __init__(self,
+                 filenames: List[str],
+                 num_epochs: int,
+                 num_trainers: int,
+                 batch_size: int,
+                 rank: int,
+                 drop_last: bool = False,
+                 num_reducers: int = None,
+                 max_concurrent_epochs: int = 2,
+                 *,
+                 seed: Optional[int] = None,
+                 backend: Optional[str] = None,
+                 output: Optional[str] = None,
+                 layout_fn=None,
+                 queue_name: Optional[str] = None,
+                 start_epoch: int = 0,
+                 stats_collector=None,
+                 chunk_wait_timeout_s: Optional[float] = None,
+                 **engine_options):
+        if num_reducers is None:
+            num_reducers = int(
+                num_trainers * get_num_cpus() * REDUCER_CLUSTER_CORE_SHARE)
+        num_reducers = max(1, num_reducers)
+        max_concurrent_epochs = max(1, min(max_concurrent_epochs, max(1, num_epochs)))
+
+        self._batch_size = batch_size
+        self._num_epochs = num_epochs
+        self._num_trainers = num_trainers
+        self._rank = rank
+        self._epoch = None
+        # Used to check that the user is correctly setting the epoch at the
+        # beginning of each epoch.
+        self._last_epoch = None
+        self._drop_last = drop_last
+        self._wait_timeout = chunk_wait_timeout_s
+        self._skip_batches = 0
+        self._batches_consumed = 0
+        self._engine = None
+        self._driver: Optional[threading.Thread] = None
+        self._driver_error: List[BaseException] = []
+        self._shuffle_duration = None
+
+        ctx = bootstrap.current_context()
+        distributed = ctx.world > 1 and ctx.world == num_trainers
+        owner = distributed or rank == 0
+        name = queue_name or BATCHQUEUE_ACTOR_NAME
+        if distributed:
+            if rank != ctx.rank:
+                raise ValueError(f"rank={rank} does not match the process group "
+                                 f"rank {ctx.rank}")
+            name = f"{name}:{rank}"
+
+        if owner:
+            # Owner process: build the engine, the queue and kick off shuffling.
+            from ray_shuffling_data_loader_b200.runtime.engine import make_engine
+            self._engine = make_engine(
+                filenames, num_trainers=num_trainers, num_reducers=num_reducers,
+                batch_size=batch_size, drop_last=drop_last, layout_fn=layout_fn,
+                seed=seed, backend=backend, stats_collector=stats_collector,
+                max_concurrent_epochs=max_concurrent_epochs, **engine_options)
+            self._seed = self._engine.seed
+            self._batch_queue = BatchQueue(
+                num_epochs, num_trainers, max_concurrent_epochs,
+                name=name, connect=False,
+                active_ranks=self._engine.local_trainers)
+            self._consumer = BatchConsumerQueue(self._batch_queue)
+            # Wait until the queue has been created.
+            self._batch_queue.ready()
+            # Kick off shuffle on the driver thread.
+            self._driver = threading.Thread(
+                target=self._drive, name=f"shuffle-driver[{rank}]", daemon=True,
+                args=(filenames, num_epochs, num_reducers, num_trainers,
+                      stats_collector, start_epoch))
+            self._driver.start()
+            device = self._engine.device
+        else:
+            # Worker process/instance: connect to the batch queue.
+            self._batch_queue = BatchQueue(
+                num_epochs, num_trainers, max_concurrent_epochs,
+                name=name, connect=True)
+            self._seed = seed
+            device = "cpu"
+        if output is None:
+            output = "pandas" if device == "cpu" else "device"
+        if output not in ("pandas", "device", "packed"):
+            raise ValueError(f"unknown output {output!r}")
+        self._output = output
+
+    # ------------------------------------------------------------------
+    def _drive(self, filenames, num_epochs, num_reducers, num_trainers,
+               stats_collector, start_epoch):
+        try:
+            self._shuffle_duration = shuffle(
+                filenames, self._consumer, num_epochs, num_reducers,
+                num_trainers, stats_collector=stats_collector,
+                engine=self._engine, start_epoch=start_epoch)
+        except BaseException as e:  # re-raised in the consumer thread
+            self._driver_error.append(e)
+            try:
+                self._batch_queue.shutdown()
+            except Exception:
+                pass
+
+    @property
+    def engine(self):
+        return self._engine
+
+    @property
+    def seed(self):
+        return self._seed
+
+    def set_epoch(self, epoch):
+        """
+        Set the current training epoch. This should be called before
+        constructing the iterator on this dataset (e.g. before the
+        enumerate(train_loader) call).
+
+        Args:
+            epoch (int) The epoch number for the training epoch that is about
+                to start.
+        """
+        self._epoch = epoch
+
+    # -- checkpoint / resume (not in the reference) -------------------------
+    def state_dict(self) -> dict:
+        return {"seed": self._seed, "epoch": self._epoch,
+                "batches_consumed": self._batches_consumed,
+                "batch_size": self._batch_size}
+
+    def load_state_dict(self, state: dict) -> None:
+        """Resume inside ``state['epoch']``: construct the dataset with the same
+        ``seed`` and ``start_epoch=state['epoch']``, load the state, call
+        ``set_epoch(state['epoch'])`` and iterate - the first
+        ``batches_consumed`` batches are skipped."""
+        if self._seed is not None and state.get("seed") not in (None, self._seed):
+            raise ValueError("state_dict seed does not match this dataset's seed")
+        if state.get("batch_size", self._batch_size) != self._batch_size:
+            raise ValueError("state_dict batch_size mismatch")
+        self._skip_batches = int(state.get("batches_consumed", 0))
+
+    def _convert(self, packed, layout):
+        if self._output == "packed":
+            return packed
+        if self._output == "device":
+            return DeviceBatch(packed, layout)
+        return packed_to_dataframe(_to_numpy(packed), layout)
+
+    def _raise_driver_error(self):
+        if self._driver_error:
+            raise RuntimeError("shuffle driver failed") from self._driver_error[0]
+
+    def __iter__(self):
+        """
+        This iterator yields batches from the shuffling queue.
+        """
+        if self._epoch is None or self._epoch == self._last_epoch:
+            raise ValueError(
+                "You must set the epoch on this dataset via set_epoch()"
+                "at the beginning of each epoch, before iterating over this "
+                "dataset (e.g. via enumerate(ds)).")
+        epoch = self._epoch
+        rebatch = _Rebatcher(self._batch_size)
+        self._batches_consumed = 0
+        skip = self._skip_batches
+        self._skip_batches = 0
+        buffers = {}
+        layout = None
+        is_done = False
+        finished = False
+        unacked = 0
+        try:
+            while not is_done:
+                # Get a batch of reducer chunks from the queue.
+                try:
+                    pending = self._batch_queue.get_batch(self._rank, epoch)
+                except Exception:
+                    self._raise_driver_error()
+                    raise
+                if pending and pending[-1] is None:
+                    # Set done flag but don't break yet, since we might still
+                    # have more items in pending to consume.
+                    is_done = True
+                    pending.pop()
+                num_outstanding = unacked = len(pending)
+                for chunk in pending:
+                    chunk.wait(self._wait_timeout)
+                    layout = chunk.layout
+                    buffers[id(chunk.buffer)] = chunk.buffer
+                    rebatch.push(chunk)
+                    for packed in rebatch.pop_full():
+                        self._batches_consumed += 1
+                        if skip > 0:
+                            skip -= 1
+                            continue
+                        yield self._convert(packed, layout)
+                if num_outstanding > 0:
+                    # Signal to the queue that we're done with these chunks.
+                    self._batch_queue.task_done(self._rank, epoch, num_outstanding)
+                    unacked = 0
+            # Yield leftover (incomplete) batch if we're not dropping
+            # incomplete batches.
+            tail = rebatch.pop_tail()
+            if tail is not None and not self._drop_last:
+                self._batches_consumed += 1
+                if skip <= 0:
+                    yield self._convert(tail, layout)
+            finished = True
+        finally:
+            if unacked:
+                # Abandoned mid-group (early ``break``): acknowledge what we hold.
+                try:
+                    self._batch_queue.task_done(self._rank, epoch, unacked)
+                except Exception:
+                    pass
+            if not finished and not is_done:
+                self._drain(epoch)
+            for buf in buffers.values():
+                buf.release()
+            if finished or is_done:
+                # Account for the producer_done sentinel.
+                try:
+                    self._batch_queue.task_done(self._rank, epoch, 1)
+                except Exception:
+                    pass
+            self._last_epoch = epoch
+        if epoch == self._num_epochs - 1:
+            self._finish()
+
+    def _drain(self, epoch):
+        """The consumer abandoned the epoch early: swallow the rest so the
+        epoch window (and every other rank) keeps moving."""
+        try:
+            while True:
+                pending = self._batch_queue.get_batch(self._rank, epoch)
+                done = bool(pending) and pending[-1] is None
+                self._batch_queue.task_done(self._rank, epoch, len(pending))
+                if done:
+                    return
+        except Exception:
+            return
+
+    def _finish(self):
+        if self._engine is None:
+            return      # a connected worker never owns the queue
+        if self._driver is not None:
+            # Returns once every trainer has consumed the final epoch.
+            self._driver.join()
+            self._raise_driver_error()
+            self._driver = None
+        self._engine.close()
+        try:
+            self._batch_queue.shutdown()
+        except Exception:
+            pass
+
+    def close(self):
+        """Tear down early (the last epoch's iterator does this itself)."""
+        if self._engine is None:
+            return
+        try:
+            self._batch_queue.shutdown()
+        except Exception:
+            pass
+        if self._driver is not None:
+            self._driver.join(timeout=30)
+            self._driver = None
+        if self._engine is not None:
+            self._engine.close()
+
+
+class _Rebatcher:
+    """Carve exact ``batch_size`` batches out of successive chunks.
+
+    Adjacent chunks of the same epoch buffer are merged into one span, so a
+    batch that straddles a chunk boundary is still a zero-copy view; only chunks
+    living in different buffers (a remote, pickled chunk) are concatenated."""
+
+    def __init__(self, batch_size: int):
+        self.batch_size = batch_size
+        self.spans = []     # [buffer, start, stop]
+        self.rows = 0
+
+    def push(self, chunk: ShuffledChunk):
+        if len(chunk) == 0:
+            return
+        if self.spans and self.spans[-1][0] is chunk.buffer \
+                and self.spans[-1][2] == chunk.row_start:
+            self.spans[-1][2] = chunk.row_stop
+        else:
+            self.spans.append([chunk.buffer, chunk.row_start, chunk.row_stop])
+        self.rows += len(chunk)
+
+    def _take(self, n: int):
+        pieces = []
+        while n > 0:
+            buf, start, stop = self.spans[0]
+            k = min(n, stop - start)
+            pieces.append(buf.view(start, start + k))
+            if start + k == stop:
+                self.spans.pop(0)
+            else:
+                self.spans[0][1] = start + k
+            n -= k
+            self.rows -= k
+        if len(pieces) == 1:
+            return pieces[0]
+        import numpy as np
+        if isinstance(pieces[0], np.ndarray):
+            return np.concatenate(pieces, axis=0)
+        import torch
+        return torch.cat(pieces, dim=0)
+
+    def pop_full(self):
+        while self.rows >= self.batch_size:
+            yield self._take(self.batch_size)
+
+    def pop_tail(self):
+        return self._take(self.rows) if self.rows > 0 else None
+
+
+class BatchConsumerQueue(BatchConsumer):
+    def __init__(self, batch_queue: BatchQueue):
+        self._batch_queue = batch_queue
+
+    def consume(self, rank: int, epoch: int, batches: List[ShuffledChunk]):
+        self._batch_queue.put_batch(rank, epoch, batches)
+
+    def producer_done(self, rank: int, epoch: int):
+        self._batch_queue.producer_done(rank, epoch)
+
+    def wait_until_ready(self, epoch: int):
+        self._batch_queue.new_epoch(epoch)
+
+    def wait_until_all_epochs_done(self):
+        self._batch_queue.wait_until_all_epochs_done()
+
+
+def _smoke_main():
+    """``python -m ray_shuffling_data_loader_b200.dataset``: the reference's
+    smoke driver (``dataset.py:208-252``), with assertions added."""
+    import shutil
+    import tempfile
+    from ray_shuffling_data_loader_b200.stats import human_readable_size
+    from ray_shuffling_data_loader_b200.data_generation import generate_data
+    num_rows = 10**6
+    num_files = 10
+    num_row_groups_per_file = 1
+    max_row_group_skew = 0.0
+    data_dir = tempfile.mkdtemp()
+    print(f"Generating {num_rows} rows over {num_files} files, with "
+          f"{num_row_groups_per_file} row groups per file and at most "
+          f"{100 * max_row_group_skew:.1f}% row group skew.")
+    filenames, num_bytes = generate_data(num_rows, num_files,
+                                         num_row_groups_per_file,
+                                         max_row_group_skew, data_dir)
+    print(f"Generated {len(filenames)} files containing {num_rows} rows "
+          f"with {num_row_groups_per_file} row groups per file, totalling "
+          f"{human_readable_size(num_bytes)}.")
+    num_epochs = 4
+    num_trainers = 1
+    batch_size = 20000
+    rank = 0
+    num_reducers = 8
+    print(f"Creating shuffling dataset with {batch_size} batch size, "
+          f"{num_epochs} epochs, {num_reducers} reducers, and {num_trainers} "
+          "trainers.")
+    print(f"Should consume {num_rows // batch_size} batches.")
+    ds = ShufflingDataset(filenames, num_epochs, num_trainers, batch_size, rank,
+                          num_reducers=num_reducers)
+    for epoch in range(num_epochs):
+        ds.set_epoch(epoch)
+        rows = 0
+        for batch_idx, batch in enumerate(ds):
+            rows += len(batch)
+            print(f"Consuming batch {batch_idx}!")
+        assert rows == num_rows, (rows, num_rows)
+    print("Done consuming batches.")
+    shutil.rmtree(data_dir)
+
+
+if __name__ == "__main__":
+    _smoke_main()

@@ -1,0 +1,166 @@
+"""CPU (numpy) shuffle engine: the semantic reference for the device engine.
+
+Implements exactly the pipeline the CUDA engine implements - ingest the rows
+this process owns once, then per epoch evaluate ``pi_e`` for every local row,
+split positions into (trainer, slot) and write the cast+packed row into the
+destination trainer's epoch buffer - with numpy on the host and, when several
+processes cooperate, a gloo ``all_to_all`` for the row exchange. It is both the
+no-GPU backend (BASELINE.json config 1: "ShufflingDataset num_trainers=1
+num_reducers=2 on CPU") and the golden model the GPU tests diff against
+byte for byte.
+
+Replaces reference ``shuffle_map``/``shuffle_reduce`` (``shuffle.py:129-200``):
+no per-epoch Parquet re-read, no R boolean-mask passes, no concat, no second
+permutation pass.
+"""
+from __future__ import annotations
+
+import os
+import threading
+import timeit
+from concurrent.futures import ThreadPoolExecutor
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from ray_shuffling_data_loader_b200.ops import layout as L
+from ray_shuffling_data_loader_b200.ops import perm
+from ray_shuffling_data_loader_b200.ops.plan import ShufflePlan
+from ray_shuffling_data_loader_b200.runtime import ingest
+from ray_shuffling_data_loader_b200.runtime.chunks import EpochBuffer
+
+
+class CpuShuffleEngine:
+    """See module docstring. ``world``/``rank`` describe cooperating processes
+    (gloo); with ``world == 1`` this process serves every trainer."""
+
+    device = "cpu"
+
+    def __init__(self, filenames: Sequence[str], plan_args: dict,
+                 layout_fn, seed: int, rank: int = 0, world: int = 1,
+                 stats_collector=None, num_threads: Optional[int] = None,
+                 process_group=None, index: Optional[ingest.DatasetIndex] = None):
+        self.index = index or ingest.scan_files(filenames)
+        self.plan = ShufflePlan(num_rows=self.index.num_rows, **plan_args)
+        if world > 1 and self.plan.num_trainers != world:
+            raise ValueError("distributed mode needs num_trainers == world size")
+        self.layout: L.RowLayout = layout_fn(self.index.schema)
+        self.seed = int(seed)
+        self.rank = rank
+        self.world = world
+        self.pg = process_group
+        self.stats = stats_collector
+        self.num_threads = num_threads or max(1, min(8, (os.cpu_count() or 2)))
+        self.local_trainers: List[int] = ([rank] if world > 1
+                                          else list(range(self.plan.num_trainers)))
+        self._pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="cpu-shuffle")
+        self._packed: Optional[np.ndarray] = None
+        self._lock = threading.Lock()
+        self._ingest_reads: List[float] = []
+        self._bytes_in_flight = 0
+        self._closed = False
+
+    # -- ingest -------------------------------------------------------------
+    def _ensure_ingested(self, epoch: int):
+        with self._lock:
+            if self._packed is not None:
+                if self.stats is not None:
+                    for _ in range(len(self.index.filenames)):
+                        self.stats.map_start(epoch)
+                        self.stats.map_done(epoch, 0.0, 0.0)
+                return
+            lo, hi = self.plan.source_range(self.rank, self.world)
+            t0 = timeit.default_timer()
+            if self.stats is not None:
+                for _ in range(len(self.index.filenames)):
+                    self.stats.map_start(epoch)
+            table = ingest.load_table(self.index, lo, hi, columns=self.layout.names,
+                                      num_threads=self.num_threads)
+            # Cast + pack once; every epoch is then a pure row permutation.
+            self._packed = L.pack_rows(table.columns, self.layout)
+            self._offset = lo
+            dur = timeit.default_timer() - t0
+            reads = table.read_durations or [0.0]
+            if self.stats is not None:
+                nfiles = len(self.index.filenames)
+                for i in range(nfiles):
+                    self.stats.map_done(epoch, dur / nfiles,
+                                        float(np.mean(reads)))
+
+    # -- one epoch ------------------------------------------------------------
+    def start_epoch(self, epoch: int) -> Dict[int, EpochBuffer]:
+        """Non-blocking: returns the epoch buffers (one per local trainer);
+        they become ready when the background shuffle has filled them."""
+        plan, layout = self.plan, self.layout
+        buffers = {}
+        for t in self.local_trainers:
+            rows = plan.trainer_rows(t)
+            data = np.empty((rows, layout.row_pitch), dtype=np.uint8)
+            buffers[t] = EpochBuffer(epoch, t, rows, layout, data, "cpu")
+            self._bytes_in_flight += data.nbytes
+        self._pool.submit(self._run_epoch, epoch, buffers)
+        return buffers
+
+    def _run_epoch(self, epoch: int, buffers: Dict[int, EpochBuffer]):
+        try:
+            self._ensure_ingested(epoch)
+            t0 = timeit.default_timer()
+            if self.stats is not None:
+                for _ in range(self.plan.num_reducers):
+                    self.stats.reduce_start(epoch)
+            key = perm.make_key(self.plan.num_rows, self.seed, epoch)
+            n_local = self._packed.shape[0]
+            gidx = np.arange(self._offset, self._offset + n_local, dtype=np.uint64)
+            pos = perm.permute(gidx, key)
+            trainer, slot = self.plan.position_to_trainer(pos)
+            if self.world == 1:
+                for t, buf in buffers.items():
+                    sel = np.nonzero(trainer == t)[0]
+                    buf.data[slot[sel]] = self._packed[sel]
+            else:
+                self._exchange(trainer, slot, buffers[self.rank])
+            dur = timeit.default_timer() - t0
+            if self.stats is not None:
+                for _ in range(self.plan.num_reducers):
+                    self.stats.reduce_done(epoch, dur / self.plan.num_reducers)
+            for buf in buffers.values():
+                buf.mark_ready()
+        except BaseException as e:  # surface in the consumer, not the pool
+            for buf in buffers.values():
+                buf.mark_ready(e)
+
+    def _exchange(self, trainer: np.ndarray, slot: np.ndarray, buf: EpochBuffer):
+        """Row exchange over gloo: the host analogue of the NVLink scatter."""
+        import torch
+        import torch.distributed as dist
+        pitch = self.layout.row_pitch
+        order = np.argsort(trainer, kind="stable")
+        counts = np.bincount(trainer, minlength=self.world).astype(np.int64)
+        send_rows = torch.from_numpy(np.ascontiguousarray(self._packed[order]))
+        send_slots = torch.from_numpy(np.ascontiguousarray(slot[order]))
+        in_counts = torch.from_numpy(counts)
+        out_counts = torch.empty_like(in_counts)
+        dist.all_to_all_single(out_counts, in_counts, group=self.pg)
+        recv_n = int(out_counts.sum())
+        recv_rows = torch.empty((recv_n, pitch), dtype=torch.uint8)
+        recv_slots = torch.empty(recv_n, dtype=torch.int64)
+        osz, isz = out_counts.tolist(), counts.tolist()
+        dist.all_to_all_single(recv_rows, send_rows, osz, isz, group=self.pg)
+        dist.all_to_all_single(recv_slots, send_slots, osz, isz, group=self.pg)
+        buf.data[recv_slots.numpy()] = recv_rows.numpy()
+
+    # -- lifecycle ----------------------------------------------------------
+    def release_epoch(self, epoch: int, buffers: Dict[int, EpochBuffer]):
+        for b in buffers.values():
+            if b.data is not None:
+                self._bytes_in_flight -= getattr(b.data, "nbytes", 0)
+
+    def bytes_in_use(self) -> int:
+        base = self._packed.nbytes if self._packed is not None else 0
+        return base + max(0, self._bytes_in_flight)
+
+    def close(self):
+        if not self._closed:
+            self._closed = True
+            self._pool.shutdown(wait=True)
+            self._packed = None
