@@ -1,0 +1,402 @@
+// Python bindings + host runtime for the B200 shuffle engine.
+//
+// This is the native replacement for the roles the reference delegates to Ray
+// (SURVEY.md 2.2): HBM arenas and pinned staging (plasma object store), CUDA-IPC
+// peer mapping (object manager / named-actor directory), streams + events
+// (task scheduler), epoch-tagged signal words (actor RPC), and a host thread
+// pool for staging copies. Only the CUDA runtime is linked (statically); no
+// libtorch dependency, tensors are exchanged as raw device pointers.
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <queue>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "kernels.h"
+
+namespace py = pybind11;
+using rsdl::FastParams;
+using rsdl::FieldDev;
+using rsdl::FlagTargets;
+using rsdl::GenericParams;
+
+namespace {
+
+inline void check(cudaError_t e, const char* what) {
+  if (e != cudaSuccess)
+    throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+template <typename T> T* as_ptr(uintptr_t v) { return reinterpret_cast<T*>(v); }
+inline cudaStream_t as_stream(uintptr_t v) { return reinterpret_cast<cudaStream_t>(v); }
+inline cudaEvent_t as_event(uintptr_t v) { return reinterpret_cast<cudaEvent_t>(v); }
+
+PermKeyDev make_key(const std::vector<uint64_t>& w) {
+  // (n, bits_l, bits_r, k0..k5) - ops/perm.py::PermKey.as_words
+  if (w.size() != 3 + RSDL_PERM_ROUNDS) throw std::runtime_error("bad permutation key");
+  PermKeyDev k;
+  k.n = w[0];
+  const uint32_t bits_l = static_cast<uint32_t>(w[1]);
+  k.bits_r = static_cast<uint32_t>(w[2]);
+  k.mask_l = bits_l >= 32 ? 0xFFFFFFFFu : ((1u << bits_l) - 1u);
+  k.mask_r = k.bits_r >= 32 ? 0xFFFFFFFFu : ((1u << k.bits_r) - 1u);
+  for (int i = 0; i < RSDL_PERM_ROUNDS; ++i) k.k[i] = static_cast<uint32_t>(w[3 + i]);
+  return k;
+}
+
+PlanDev make_plan(uint64_t num_rows, uint32_t num_trainers) {
+  PlanDev p;
+  p.q = num_rows / num_trainers;
+  p.rem = static_cast<uint32_t>(num_rows % num_trainers);
+  p.big = static_cast<unsigned long long>(p.rem) * (p.q + 1);
+  p.num_trainers = num_trainers;
+  return p;
+}
+
+template <typename P>
+void fill_dst(P& p, const std::vector<uintptr_t>& dst) {
+  if (dst.size() > RSDL_MAX_TRAINERS) throw std::runtime_error("too many trainers");
+  for (size_t i = 0; i < RSDL_MAX_TRAINERS; ++i)
+    p.dst[i] = i < dst.size() ? as_ptr<uint8_t>(dst[i]) : nullptr;
+}
+
+// ---------------------------------------------------------------------------
+// Host worker pool: parallel staging copies (pageable -> pinned) off the GIL.
+// ---------------------------------------------------------------------------
+class HostPool {
+ public:
+  explicit HostPool(int n) : stop_(false) {
+    for (int i = 0; i < std::max(1, n); ++i) workers_.emplace_back([this] { run(); });
+  }
+  ~HostPool() {
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+  int size() const { return static_cast<int>(workers_.size()); }
+
+  // Split [0, nbytes) into chunks, copy them on the workers, wait for all.
+  void parallel_memcpy(void* dst, const void* src, size_t nbytes) {
+    const size_t chunk = std::max<size_t>(1 << 20, nbytes / (workers_.size() * 4) + 1);
+    std::atomic<size_t> pending{0};
+    std::mutex done_mu;
+    std::condition_variable done_cv;
+    size_t launched = 0;
+    for (size_t off = 0; off < nbytes; off += chunk) ++launched;
+    pending = launched;
+    for (size_t off = 0; off < nbytes; off += chunk) {
+      const size_t len = std::min(chunk, nbytes - off);
+      submit([=, &pending, &done_mu, &done_cv] {
+        std::memcpy(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, len);
+        if (pending.fetch_sub(1) == 1) {
+          std::lock_guard<std::mutex> g(done_mu);
+          done_cv.notify_all();
+        }
+      });
+    }
+    std::unique_lock<std::mutex> lk(done_mu);
+    done_cv.wait(lk, [&] { return pending.load() == 0; });
+  }
+
+ private:
+  void submit(std::function<void()> fn) {
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      tasks_.push(std::move(fn));
+    }
+    cv_.notify_one();
+  }
+  void run() {
+    for (;;) {
+      std::function<void()> fn;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [this] { return stop_ || !tasks_.empty(); });
+        if (stop_ && tasks_.empty()) return;
+        fn = std::move(tasks_.front());
+        tasks_.pop();
+      }
+      fn();
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::queue<std::function<void()>> tasks_;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  bool stop_;
+};
+
+// ---------------------------------------------------------------------------
+// Flag polling on the host: the blocking half of the device ring (K11).
+// ---------------------------------------------------------------------------
+class FlagPoller {
+ public:
+  FlagPoller() {
+    check(cudaHostAlloc(reinterpret_cast<void**>(&scratch_), RSDL_MAX_TRAINERS * sizeof(uint32_t),
+                        cudaHostAllocDefault), "cudaHostAlloc(flag scratch)");
+    check(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate(flag)");
+  }
+  ~FlagPoller() {
+    cudaStreamDestroy(stream_);
+    cudaFreeHost(scratch_);
+  }
+  // Returns the index of the first flag still below `value` after `timeout_s`
+  // seconds, or -1 once all `count` flags are >= value (wrap-safe compare).
+  int wait(const uint32_t* dev_flags, uint32_t count, uint32_t value, double timeout_s) {
+    if (count > RSDL_MAX_TRAINERS) throw std::runtime_error("too many flags");
+    const auto t0 = std::chrono::steady_clock::now();
+    int sleep_us = 5;
+    for (;;) {
+      check(cudaMemcpyAsync(scratch_, dev_flags, count * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                            stream_), "cudaMemcpyAsync(flags)");
+      check(cudaStreamSynchronize(stream_), "cudaStreamSynchronize(flags)");
+      int lagging = -1;
+      for (uint32_t i = 0; i < count; ++i)
+        if (static_cast<int32_t>(scratch_[i] - value) < 0) { lagging = static_cast<int>(i); break; }
+      if (lagging < 0) return -1;
+      const double waited =
+          std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      if (timeout_s >= 0 && waited > timeout_s) return lagging;
+      std::this_thread::sleep_for(std::chrono::microseconds(sleep_us));
+      if (sleep_us < 200) sleep_us *= 2;
+    }
+  }
+  std::vector<uint32_t> read(const uint32_t* dev_flags, uint32_t count) {
+    check(cudaMemcpyAsync(scratch_, dev_flags, count * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                          stream_), "cudaMemcpyAsync(flags)");
+    check(cudaStreamSynchronize(stream_), "cudaStreamSynchronize(flags)");
+    return std::vector<uint32_t>(scratch_, scratch_ + count);
+  }
+
+ private:
+  uint32_t* scratch_ = nullptr;
+  cudaStream_t stream_ = nullptr;
+};
+
+}  // namespace
+
+PYBIND11_MODULE(_C, m) {
+  m.doc() = "ray_shuffling_data_loader_b200 native runtime (sm_100a)";
+  m.attr("MAX_TRAINERS") = RSDL_MAX_TRAINERS;
+  m.attr("TILE_ROWS") = rsdl::fast_tile_rows();
+  m.def("fast_panel_cols", &rsdl::fast_panel_cols);
+
+  // ---- device -----------------------------------------------------------
+  m.def("device_count", [] { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0; });
+  m.def("set_device", [](int d) { check(cudaSetDevice(d), "cudaSetDevice"); });
+  m.def("get_device", [] { int d; check(cudaGetDevice(&d), "cudaGetDevice"); return d; });
+  m.def("sm_count", [](int d) {
+    int v; check(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d), "attr"); return v; });
+  m.def("compute_capability", [](int d) {
+    int a, b;
+    check(cudaDeviceGetAttribute(&a, cudaDevAttrComputeCapabilityMajor, d), "attr");
+    check(cudaDeviceGetAttribute(&b, cudaDevAttrComputeCapabilityMinor, d), "attr");
+    return std::make_pair(a, b); });
+  m.def("mem_get_info", [] {
+    size_t f, t; check(cudaMemGetInfo(&f, &t), "cudaMemGetInfo"); return std::make_pair(f, t); });
+  m.def("can_access_peer", [](int a, int b) {
+    int v = 0; check(cudaDeviceCanAccessPeer(&v, a, b), "cudaDeviceCanAccessPeer"); return v != 0; });
+  m.def("device_synchronize", [] {
+    py::gil_scoped_release r; check(cudaDeviceSynchronize(), "cudaDeviceSynchronize"); });
+
+  // ---- memory: HBM arenas, pinned staging, CUDA IPC --------------------------
+  m.def("device_malloc", [](size_t n) {
+    void* p = nullptr; check(cudaMalloc(&p, std::max<size_t>(n, 256)), "cudaMalloc");
+    return reinterpret_cast<uintptr_t>(p); });
+  m.def("device_free", [](uintptr_t p) { check(cudaFree(as_ptr<void>(p)), "cudaFree"); });
+  m.def("device_memset_async", [](uintptr_t p, int v, size_t n, uintptr_t s) {
+    check(cudaMemsetAsync(as_ptr<void>(p), v, n, as_stream(s)), "cudaMemsetAsync"); });
+  m.def("pinned_alloc", [](size_t n) {
+    void* p = nullptr;
+    py::gil_scoped_release r;
+    check(cudaHostAlloc(&p, std::max<size_t>(n, 64), cudaHostAllocDefault), "cudaHostAlloc");
+    return reinterpret_cast<uintptr_t>(p); });
+  m.def("pinned_free", [](uintptr_t p) { check(cudaFreeHost(as_ptr<void>(p)), "cudaFreeHost"); });
+  m.def("host_register", [](uintptr_t p, size_t n) {
+    check(cudaHostRegister(as_ptr<void>(p), n, cudaHostRegisterDefault), "cudaHostRegister"); });
+  m.def("host_unregister", [](uintptr_t p) {
+    check(cudaHostUnregister(as_ptr<void>(p)), "cudaHostUnregister"); });
+  m.def("ipc_get_handle", [](uintptr_t p) {
+    cudaIpcMemHandle_t h;
+    check(cudaIpcGetMemHandle(&h, as_ptr<void>(p)), "cudaIpcGetMemHandle");
+    return py::bytes(reinterpret_cast<const char*>(&h), sizeof(h)); });
+  m.def("ipc_open_handle", [](const std::string& b) {
+    if (b.size() != sizeof(cudaIpcMemHandle_t)) throw std::runtime_error("bad IPC handle");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, b.data(), sizeof(h));
+    void* p = nullptr;
+    check(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+    return reinterpret_cast<uintptr_t>(p); });
+  m.def("ipc_close_handle", [](uintptr_t p) {
+    check(cudaIpcCloseMemHandle(as_ptr<void>(p)), "cudaIpcCloseMemHandle"); });
+  m.def("enable_peer_access", [](int peer) {
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return; }
+    check(e, "cudaDeviceEnablePeerAccess"); });
+
+  // ---- copies ------------------------------------------------------------
+  m.def("memcpy_async", [](uintptr_t dst, uintptr_t src, size_t n, int kind, uintptr_t s) {
+    check(cudaMemcpyAsync(as_ptr<void>(dst), as_ptr<void>(src), n,
+                          static_cast<cudaMemcpyKind>(kind), as_stream(s)), "cudaMemcpyAsync"); });
+  m.def("memcpy2d_async", [](uintptr_t dst, size_t dpitch, uintptr_t src, size_t spitch,
+                             size_t width, size_t height, int kind, uintptr_t s) {
+    check(cudaMemcpy2DAsync(as_ptr<void>(dst), dpitch, as_ptr<void>(src), spitch, width, height,
+                            static_cast<cudaMemcpyKind>(kind), as_stream(s)), "cudaMemcpy2DAsync"); });
+  m.attr("H2D") = static_cast<int>(cudaMemcpyHostToDevice);
+  m.attr("D2H") = static_cast<int>(cudaMemcpyDeviceToHost);
+  m.attr("D2D") = static_cast<int>(cudaMemcpyDeviceToDevice);
+
+  // ---- streams & events ----------------------------------------------------
+  m.def("stream_priority_range", [] {
+    int lo, hi; check(cudaDeviceGetStreamPriorityRange(&lo, &hi), "priority range");
+    return std::make_pair(lo, hi); });
+  m.def("stream_create", [](int priority) {
+    cudaStream_t s;
+    check(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, priority), "cudaStreamCreate");
+    return reinterpret_cast<uintptr_t>(s); });
+  m.def("stream_destroy", [](uintptr_t s) { check(cudaStreamDestroy(as_stream(s)), "cudaStreamDestroy"); });
+  m.def("stream_synchronize", [](uintptr_t s) {
+    py::gil_scoped_release r; check(cudaStreamSynchronize(as_stream(s)), "cudaStreamSynchronize"); });
+  m.def("stream_query", [](uintptr_t s) {
+    cudaError_t e = cudaStreamQuery(as_stream(s));
+    if (e == cudaErrorNotReady) return false;
+    check(e, "cudaStreamQuery"); return true; });
+  m.def("stream_wait_event", [](uintptr_t s, uintptr_t e) {
+    check(cudaStreamWaitEvent(as_stream(s), as_event(e), 0), "cudaStreamWaitEvent"); });
+  m.def("event_create", [](bool timing) {
+    cudaEvent_t e;
+    check(cudaEventCreateWithFlags(&e, timing ? cudaEventDefault : cudaEventDisableTiming),
+          "cudaEventCreate");
+    return reinterpret_cast<uintptr_t>(e); });
+  m.def("event_destroy", [](uintptr_t e) { check(cudaEventDestroy(as_event(e)), "cudaEventDestroy"); });
+  m.def("event_record", [](uintptr_t e, uintptr_t s) {
+    check(cudaEventRecord(as_event(e), as_stream(s)), "cudaEventRecord"); });
+  m.def("event_synchronize", [](uintptr_t e) {
+    py::gil_scoped_release r; check(cudaEventSynchronize(as_event(e)), "cudaEventSynchronize"); });
+  m.def("event_query", [](uintptr_t e) {
+    cudaError_t r = cudaEventQuery(as_event(e));
+    if (r == cudaErrorNotReady) return false;
+    check(r, "cudaEventQuery"); return true; });
+  m.def("event_elapsed_ms", [](uintptr_t a, uintptr_t b) {
+    float ms = 0; check(cudaEventElapsedTime(&ms, as_event(a), as_event(b)), "cudaEventElapsedTime");
+    return ms; });
+
+  // ---- kernels ---------------------------------------------------------------
+  m.def("scatter_fast",
+        [](const std::vector<uint64_t>& key, uint64_t num_rows, uint32_t num_trainers,
+           uintptr_t cols, uint32_t num_cols, uint64_t n_local, uint64_t global_offset,
+           uint32_t row_pitch, uint32_t scale_offset, const std::vector<uintptr_t>& dst, int mode,
+           int grid, uintptr_t stream) {
+          FastParams p;
+          p.key = make_key(key);
+          p.plan = make_plan(num_rows, num_trainers);
+          p.cols = as_ptr<const uint8_t* const>(cols);
+          p.num_cols = num_cols;
+          const uint32_t panel = static_cast<uint32_t>(rsdl::fast_panel_cols(mode));
+          p.num_panels = (num_cols + panel - 1) / panel;
+          p.n_local = n_local;
+          p.global_offset = global_offset;
+          p.row_pitch = row_pitch;
+          p.scale_offset = scale_offset;
+          fill_dst(p, dst);
+          rsdl::launch_scatter_fast(p, mode, grid, as_stream(stream));
+        },
+        py::arg("key"), py::arg("num_rows"), py::arg("num_trainers"), py::arg("cols"),
+        py::arg("num_cols"), py::arg("n_local"), py::arg("global_offset"), py::arg("row_pitch"),
+        py::arg("scale_offset"), py::arg("dst"), py::arg("mode"), py::arg("grid"),
+        py::arg("stream"));
+  m.def("scatter_generic",
+        [](const std::vector<uint64_t>& key, uint64_t num_rows, uint32_t num_trainers,
+           uintptr_t fields, uint32_t num_fields, uint64_t n_local, uint64_t global_offset,
+           uint32_t row_pitch, uint32_t write_lo, uint32_t write_hi,
+           const std::vector<uintptr_t>& dst, int grid, uintptr_t stream) {
+          GenericParams p;
+          p.key = make_key(key);
+          p.plan = make_plan(num_rows, num_trainers);
+          p.fields = as_ptr<const FieldDev>(fields);
+          p.num_fields = num_fields;
+          p.rows_per_block = 0;
+          p.n_local = n_local;
+          p.global_offset = global_offset;
+          p.row_pitch = row_pitch;
+          p.write_lo = write_lo;
+          p.write_hi = write_hi;
+          fill_dst(p, dst);
+          rsdl::launch_scatter_generic(p, grid, as_stream(stream));
+        },
+        py::arg("key"), py::arg("num_rows"), py::arg("num_trainers"), py::arg("fields"),
+        py::arg("num_fields"), py::arg("n_local"), py::arg("global_offset"),
+        py::arg("row_pitch"), py::arg("write_lo"), py::arg("write_hi"), py::arg("dst"),
+        py::arg("grid"), py::arg("stream"));
+  m.attr("FIELD_DESC_BYTES") = sizeof(FieldDev);
+  m.def("perm_positions",
+        [](const std::vector<uint64_t>& key, uint64_t num_rows, uint32_t num_trainers,
+           uint64_t global_offset, uint64_t n_local, uintptr_t trainer, uintptr_t slot,
+           uintptr_t stream) {
+          rsdl::launch_perm_positions(make_key(key), make_plan(num_rows, num_trainers),
+                                      global_offset, n_local, as_ptr<int32_t>(trainer),
+                                      as_ptr<long long>(slot), as_stream(stream));
+        });
+  m.def("place_rows", [](uintptr_t rows, uintptr_t slots, uint64_t n, uint32_t pitch,
+                         uintptr_t dst, uintptr_t stream) {
+    rsdl::launch_place_rows(as_ptr<const uint8_t>(rows), as_ptr<const long long>(slots), n, pitch,
+                            as_ptr<uint8_t>(dst), as_stream(stream));
+  });
+  m.def("key_checksum", [](uintptr_t packed, uint64_t rows, uint32_t pitch, uint32_t key_off,
+                           uintptr_t out, uintptr_t stream) {
+    rsdl::launch_key_checksum(as_ptr<const uint8_t>(packed), rows, pitch, key_off,
+                              as_ptr<unsigned long long>(out), as_stream(stream));
+  });
+  m.def("batch_sum_f32", [](uintptr_t packed, uint64_t rows, uint32_t pitch, uint32_t off,
+                            uintptr_t out, uintptr_t stream) {
+    rsdl::launch_batch_sum_f32(as_ptr<const uint8_t>(packed), rows, pitch, off,
+                               as_ptr<double>(out), as_stream(stream));
+  });
+  m.def("signal_flags", [](const std::vector<uintptr_t>& ptrs, uint32_t value, uintptr_t stream) {
+    if (ptrs.size() > RSDL_MAX_TRAINERS) throw std::runtime_error("too many flag targets");
+    FlagTargets t;
+    t.count = static_cast<uint32_t>(ptrs.size());
+    for (size_t i = 0; i < RSDL_MAX_TRAINERS; ++i)
+      t.ptr[i] = i < ptrs.size() ? as_ptr<uint32_t>(ptrs[i]) : nullptr;
+    rsdl::launch_signal_flags(t, value, as_stream(stream));
+  });
+  m.def("wait_flags", [](uintptr_t flags, uint32_t count, uint32_t value, uint64_t timeout_ns,
+                         uintptr_t error, uintptr_t stream) {
+    rsdl::launch_wait_flags(as_ptr<const uint32_t>(flags), count, value, timeout_ns,
+                            as_ptr<uint32_t>(error), as_stream(stream));
+  });
+
+  // ---- host runtime objects --------------------------------------------------
+  py::class_<HostPool>(m, "HostPool")
+      .def(py::init<int>(), py::arg("num_threads"))
+      .def_property_readonly("size", &HostPool::size)
+      .def("parallel_memcpy",
+           [](HostPool& self, uintptr_t dst, uintptr_t src, size_t n) {
+             py::gil_scoped_release r;
+             self.parallel_memcpy(as_ptr<void>(dst), as_ptr<const void>(src), n);
+           });
+  py::class_<FlagPoller>(m, "FlagPoller")
+      .def(py::init<>())
+      .def("wait",
+           [](FlagPoller& self, uintptr_t flags, uint32_t count, uint32_t value, double timeout_s) {
+             py::gil_scoped_release r;
+             return self.wait(as_ptr<const uint32_t>(flags), count, value, timeout_s);
+           })
+      .def("read", [](FlagPoller& self, uintptr_t flags, uint32_t count) {
+        return self.read(as_ptr<const uint32_t>(flags), count);
+      });
+}

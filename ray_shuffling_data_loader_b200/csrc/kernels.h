@@ -1,0 +1,71 @@
+// Host-visible parameter blocks and launchers of the shuffle kernels.
+#pragma once
+
+#include <algorithm>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace rsdl {
+
+// Fast path: every source column is a 4-byte scalar (see shuffle_kernels.cu).
+struct FastParams {
+  PermKeyDev key;
+  PlanDev plan;
+  const uint8_t* const* cols;        // device array [num_cols] of column bases
+  uint32_t num_cols;
+  uint32_t num_panels;               // ceil(num_cols / panel width)
+  unsigned long long n_local;        // rows owned by this rank
+  unsigned long long global_offset;  // global index of local row 0
+  uint32_t row_pitch;                // destination row pitch (bytes)
+  uint32_t scale_offset;             // fp8 mode: byte offset of the UE8M0 scales
+  uint8_t* dst[RSDL_MAX_TRAINERS];   // epoch-slot base per trainer (local/peer)
+};
+
+struct FieldDev {
+  const uint8_t* src;
+  uint32_t src_code;
+  uint32_t dst_code;
+  uint32_t dst_off;
+  uint32_t width;
+};
+
+struct GenericParams {
+  PermKeyDev key;
+  PlanDev plan;
+  const FieldDev* fields;            // device array
+  uint32_t num_fields;
+  uint32_t rows_per_block;           // filled by the launcher
+  unsigned long long n_local;
+  unsigned long long global_offset;
+  uint32_t row_pitch;
+  uint32_t write_lo;                 // byte range of the row this launch owns
+  uint32_t write_hi;                 //   (multiples of 4; whole row by default)
+  uint8_t* dst[RSDL_MAX_TRAINERS];
+};
+
+struct FlagTargets {
+  uint32_t* ptr[RSDL_MAX_TRAINERS];
+  uint32_t count;
+};
+
+int fast_panel_cols(int mode);
+int fast_tile_rows();
+
+void launch_scatter_fast(const FastParams& p, int mode, int grid, cudaStream_t stream);
+void launch_scatter_generic(GenericParams p, int grid, cudaStream_t stream);
+void launch_perm_positions(const PermKeyDev& key, const PlanDev& plan,
+                           unsigned long long global_offset, unsigned long long n_local,
+                           int32_t* trainer, long long* slot, cudaStream_t stream);
+void launch_place_rows(const uint8_t* rows, const long long* slots, unsigned long long n,
+                       uint32_t pitch, uint8_t* dst, cudaStream_t stream);
+void launch_key_checksum(const uint8_t* packed, unsigned long long rows, uint32_t pitch,
+                         uint32_t key_off, unsigned long long* out, cudaStream_t stream);
+void launch_batch_sum_f32(const uint8_t* packed, unsigned long long rows, uint32_t pitch,
+                          uint32_t off, double* out, cudaStream_t stream);
+void launch_signal_flags(const FlagTargets& t, uint32_t value, cudaStream_t stream);
+void launch_wait_flags(const uint32_t* flags, uint32_t count, uint32_t value,
+                       unsigned long long timeout_ns, uint32_t* error, cudaStream_t stream);
+
+}  // namespace rsdl

@@ -1,0 +1,642 @@
+// Fused shuffle kernels for sm_100a (kernels K1, K2, K5, K6, K8, K11, K13 of SURVEY.md 2.4).
+//
+// What the reference does on CPUs across three Ray stages - R boolean-mask
+// partition passes per file (shuffle.py:156-161), the mapper->reducer
+// all-to-all through the object store (shuffle.py:120-123), pd.concat +
+// sample(frac=1) in the reducer (shuffle.py:192-194), re-batching
+// (dataset.py:144-168) and per-column torch.as_tensor (torch_dataset.py:209-235)
+// - is one kernel here:
+//
+//   scatter_tma_kernel    TMA bulk loads of a [cols x TILE_ROWS] tile of the
+//                         local *columnar* table into padded shared memory,
+//                         conflict-free 4x4 register transposition to row-major,
+//                         optional cast (bf16 / block-scaled e4m3), and 128 B
+//                         coalesced vector stores of every row straight into its
+//                         final (trainer, slot) - a local or a *peer* HBM address
+//                         (CUDA-IPC mapped, NVLink 5 / NVSwitch). The row's
+//                         destination comes from the Feistel bijection, computed
+//                         once per tile by the producer warp and shared with the
+//                         consumer warps through shared memory.
+//   scatter_generic_kernel mixed dtypes / list columns / arbitrary casts
+//                         (the DATA_SPEC schema), staged through shared memory.
+//
+// No NCCL call and no intermediate buffer sit on this path; NCCL all_to_all is
+// only the baseline (parallel/nccl_baseline.py).
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+
+#include "kernels.h"
+#include "perm.cuh"
+
+namespace rsdl {
+
+// ---------------------------------------------------------------------------
+// PTX helpers: mbarrier, bulk async copy (TMA, non-tensor form), vector ld/st
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// cp.async.bulk global -> shared, completion reported on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src,
+                                            uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+__device__ __forceinline__ float4 lds128(const float* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(smem_u32(p)));
+  return v;
+}
+
+// 16-byte store to a (possibly peer-mapped) global address.
+__device__ __forceinline__ void stg128(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c),
+               "r"(d)
+               : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ uint32_t f32_to_e4m3(float x) {
+  return static_cast<uint32_t>(__nv_cvt_float_to_fp8(x, __NV_SATFINITE, __NV_E4M3));
+}
+
+// Destination address of global source row `gi` (0 when the row does not exist).
+__device__ __forceinline__ unsigned long long
+dest_pointer(unsigned long long gi, const PermKeyDev& key, const PlanDev& plan,
+             uint8_t* const* dst, uint32_t row_pitch) {
+  unsigned long long pos = rsdl_permute(gi, key);
+  uint32_t trainer;
+  unsigned long long slot;
+  rsdl_position_to_dest(pos, plan, &trainer, &slot);
+  return reinterpret_cast<unsigned long long>(dst[trainer]) + slot * row_pitch;
+}
+
+// ---------------------------------------------------------------------------
+// K2 shuffle_scatter, fast path: uniform 4-byte source columns
+// ---------------------------------------------------------------------------
+//
+// Tile = TILE_ROWS consecutive local rows x up to PANEL columns. Shared memory
+// holds the tile *columnar*: column c at word offset c * P with P = TILE_ROWS+4.
+// P/4 is odd, so the 16-byte bank group of element (c, r) is (c + r/4) mod 8.
+//
+// A consumer lane owns a 4-row x FPL-column block (FPL = 16 / dst itemsize):
+// lane = (q << 2) | rho, rho = row group within a 16-row step, q = column block.
+// The 8 lanes of each LDS.128 quarter-warp are {q0, q0+1} x {rho 0..3}:
+// bank groups (FPL*q + k + rho) mod 8 are all distinct (for FPL >= 8 odd q read
+// their columns rotated by 4), so every shared load is conflict free, the 4x4
+// transposition happens in registers with static indexing, and each store
+// instruction writes, for 4 different rows, one full 128-byte line of the row.
+constexpr int kTileRows = 128;
+constexpr int kPitchWords = kTileRows + 4;   // shared-memory words per column
+constexpr int kConsumerWarps = 8;
+constexpr int kThreads = 32 * (1 + kConsumerWarps);
+
+template <int MODE> struct ModeTraits;
+template <> struct ModeTraits<0> { static constexpr int FPL = 4;  static constexpr int PANEL = 64;  static constexpr int STAGES = 4; };
+template <> struct ModeTraits<1> { static constexpr int FPL = 8;  static constexpr int PANEL = 64;  static constexpr int STAGES = 4; };
+template <> struct ModeTraits<2> { static constexpr int FPL = 16; static constexpr int PANEL = 128; static constexpr int STAGES = 3; };
+
+template <int MODE>
+struct alignas(128) FastSmem {
+  static constexpr int PANEL = ModeTraits<MODE>::PANEL;
+  static constexpr int STAGES = ModeTraits<MODE>::STAGES;
+  float tile[STAGES][PANEL * kPitchWords];
+  unsigned long long dptr[STAGES][kTileRows];
+  uint64_t full[STAGES];
+  uint64_t empty[STAGES];
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 1) scatter_tma_kernel(const FastParams p) {
+  using T = ModeTraits<MODE>;
+  constexpr int FPL = T::FPL;
+  constexpr int PANEL = T::PANEL;
+  constexpr int STAGES = T::STAGES;
+  constexpr int PASSES = PANEL / (8 * FPL);
+  extern __shared__ uint8_t smem_raw[];
+  FastSmem<MODE>& sm = *reinterpret_cast<FastSmem<MODE>*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~static_cast<uintptr_t>(127));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&sm.full[s], 1);
+      mbar_init(&sm.empty[s], kConsumerWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const unsigned long long num_tiles = (p.n_local + kTileRows - 1) / kTileRows;
+  const unsigned long long num_items = num_tiles * p.num_panels;
+
+  if (warp == 0) {
+    // ===== producer: destination pointers + TMA bulk loads =====
+    int stage = 0;
+    uint32_t phase = 0;
+    unsigned long long prev_tile = ~0ull;
+    int prev_stage = 0;
+    for (unsigned long long item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const unsigned long long tile = item / p.num_panels;
+      const uint32_t panel = static_cast<uint32_t>(item - tile * p.num_panels);
+      mbar_wait(&sm.empty[stage], phase ^ 1);
+      const unsigned long long row0 = tile * kTileRows;
+      if (tile == prev_tile) {
+        // Same rows, next column panel: reuse the shared permutation index.
+        for (int r = lane; r < kTileRows; r += 32) sm.dptr[stage][r] = sm.dptr[prev_stage][r];
+      } else {
+        for (int r = lane; r < kTileRows; r += 32) {
+          const unsigned long long lr = row0 + r;
+          sm.dptr[stage][r] = (lr < p.n_local)
+              ? dest_pointer(p.global_offset + lr, p.key, p.plan, p.dst, p.row_pitch)
+              : 0ull;
+        }
+      }
+      prev_tile = tile;
+      prev_stage = stage;
+      __syncwarp();
+      const uint32_t col0 = panel * PANEL;
+      const uint32_t ncols = min(static_cast<uint32_t>(PANEL), p.num_cols - col0);
+      if (lane == 0) mbar_arrive_expect_tx(&sm.full[stage], ncols * kTileRows * 4u);
+      __syncwarp();
+      for (uint32_t c = lane; c < ncols; c += 32) {
+        const uint8_t* src = p.cols[col0 + c] + row0 * 4ull;
+        tma_load_1d(&sm.tile[stage][c * kPitchWords], src, kTileRows * 4u, &sm.full[stage]);
+      }
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    // ===== consumers: transpose + cast + scatter =====
+    const int cwarp = warp - 1;
+    const int rho = lane & 3;
+    const int q = lane >> 2;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (unsigned long long item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const unsigned long long tile = item / p.num_panels;
+      const uint32_t panel = static_cast<uint32_t>(item - tile * p.num_panels);
+      const uint32_t col0 = panel * PANEL;
+      const uint32_t ncols = min(static_cast<uint32_t>(PANEL), p.num_cols - col0);
+      mbar_wait(&sm.full[stage], phase);
+      const float* A = sm.tile[stage];
+      for (int step = cwarp; step < kTileRows / 16; step += kConsumerWarps) {
+        const int rg = step * 4 + rho;            // 4-row group inside the tile
+        unsigned long long d[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) d[j] = sm.dptr[stage][rg * 4 + j];
+#pragma unroll
+        for (int pass = 0; pass < PASSES; ++pass) {
+          const int cb = q + 8 * pass;            // column block inside the panel
+          const uint32_t f0 = cb * FPL;
+          const bool active = f0 < ncols;
+          // (fp8 mode exchanges amax with the partner lane: nobody may skip)
+          if (MODE != 2 && !active) continue;
+          float v[FPL][4];
+#pragma unroll
+          for (int k = 0; k < FPL; ++k) {
+            // odd column blocks read rotated by 4 so that a quarter-warp's two
+            // column blocks never share a bank group when FPL is a multiple of 8
+            const int kk = (FPL >= 8) ? ((k + 4 * (q & 1)) & (FPL - 1)) : k;
+            const uint32_t f = f0 + kk;
+            float4 x = (f < ncols) ? lds128(A + f * kPitchWords + rg * 4)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (FPL >= 8 && (q & 1)) {
+              // undo the rotation with static register indices
+              v[(k + 4) & (FPL - 1)][0] = x.x; v[(k + 4) & (FPL - 1)][1] = x.y;
+              v[(k + 4) & (FPL - 1)][2] = x.z; v[(k + 4) & (FPL - 1)][3] = x.w;
+            } else {
+              v[k][0] = x.x; v[k][1] = x.y; v[k][2] = x.z; v[k][3] = x.w;
+            }
+          }
+          if (MODE == 0) {
+            const uint32_t off = (col0 + f0) * 4u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (d[j])
+                stg128(reinterpret_cast<void*>(d[j] + off), __float_as_uint(v[0][j]),
+                       __float_as_uint(v[1][j]), __float_as_uint(v[2][j]),
+                       __float_as_uint(v[3][j]));
+            }
+          } else if (MODE == 1) {
+            const uint32_t off = (col0 + f0) * 2u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (d[j])
+                stg128(reinterpret_cast<void*>(d[j] + off), pack_bf16x2(v[0][j], v[1][j]),
+                       pack_bf16x2(v[2][j], v[3][j]), pack_bf16x2(v[4][j], v[5][j]),
+                       pack_bf16x2(v[6][j], v[7][j]));
+            }
+          } else {
+            // Block-scaled e4m3: 32-element blocks = this lane + its q^1 partner.
+            const uint32_t off = col0 + f0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float amax = 0.f;
+#pragma unroll
+              for (int k = 0; k < FPL; ++k) {
+                float a = fabsf(v[k][j]);
+                amax = (a > amax) ? a : amax;      // NaN never wins: matches golden
+              }
+              amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
+              const uint32_t bits = __float_as_uint(amax * (1.0f / 448.0f));
+              int e = static_cast<int>((bits >> 23) & 0xFF) - 127 + ((bits & 0x7FFFFF) ? 1 : 0);
+              e = max(-126, min(127, e));
+              const float inv = __uint_as_float(static_cast<uint32_t>(127 - e) << 23);
+              uint32_t w[4];
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                w[g] = f32_to_e4m3(v[4 * g + 0][j] * inv) | (f32_to_e4m3(v[4 * g + 1][j] * inv) << 8) |
+                       (f32_to_e4m3(v[4 * g + 2][j] * inv) << 16) |
+                       (f32_to_e4m3(v[4 * g + 3][j] * inv) << 24);
+              }
+              if (d[j] && active) {
+                stg128(reinterpret_cast<void*>(d[j] + off), w[0], w[1], w[2], w[3]);
+                if ((q & 1) == 0) {
+                  const uint8_t sb = (amax > 0.f) ? static_cast<uint8_t>(e + 127) : 0;
+                  *reinterpret_cast<uint8_t*>(d[j] + p.scale_offset + (off >> 5)) = sb;
+                }
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.empty[stage]);
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+  }
+  // Make this CTA's peer stores visible system-wide before the grid retires
+  // (the completion flag is published by a later kernel on the same stream).
+  __threadfence_system();
+}
+
+// ---------------------------------------------------------------------------
+// K2 generic path: arbitrary per-field dtype / width / cast
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void store_cast(uint8_t* dst, uint32_t dst_code, bool is_int, long long iv,
+                                           double fv, float sv, bool from_f64) {
+  // `sv` is the exact fp32 value when the source is <= 32-bit float; `fv` the
+  // fp64 value when the source is float64; `iv` the integer value otherwise.
+  switch (dst_code) {
+    case DT_F32: {
+      float o = is_int ? static_cast<float>(iv) : (from_f64 ? __double2float_rn(fv) : sv);
+      *reinterpret_cast<float*>(dst) = o;
+      break;
+    }
+    case DT_F64: {
+      double o = is_int ? static_cast<double>(iv) : (from_f64 ? fv : static_cast<double>(sv));
+      // 8-byte fields are 8-aligned in the row but the staging pitch is odd in
+      // words: store as two halves.
+      unsigned long long b = __double_as_longlong(o);
+      reinterpret_cast<uint32_t*>(dst)[0] = static_cast<uint32_t>(b);
+      reinterpret_cast<uint32_t*>(dst)[1] = static_cast<uint32_t>(b >> 32);
+      break;
+    }
+    case DT_F16: {
+      __half o = is_int ? __ll2half_rn(iv) : (from_f64 ? __double2half(fv) : __float2half_rn(sv));
+      *reinterpret_cast<__half*>(dst) = o;
+      break;
+    }
+    case DT_BF16: {
+      float f = is_int ? static_cast<float>(iv) : (from_f64 ? __double2float_rn(fv) : sv);
+      *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn(f);
+      break;
+    }
+    case DT_FP8: {
+      float f = is_int ? static_cast<float>(iv) : (from_f64 ? __double2float_rn(fv) : sv);
+      *dst = static_cast<uint8_t>(f32_to_e4m3(f));
+      break;
+    }
+    case DT_BOOL: {
+      bool nz = is_int ? (iv != 0) : (from_f64 ? (fv != 0.0) : (sv != 0.f));
+      *dst = nz ? 1 : 0;
+      break;
+    }
+    default: {
+      long long o = is_int ? iv : (from_f64 ? static_cast<long long>(fv) : static_cast<long long>(sv));
+      switch (dst_code) {
+        case DT_U8: case DT_I8: *dst = static_cast<uint8_t>(o); break;
+        case DT_I16: *reinterpret_cast<int16_t*>(dst) = static_cast<int16_t>(o); break;
+        case DT_I32: *reinterpret_cast<int32_t*>(dst) = static_cast<int32_t>(o); break;
+        default:
+          reinterpret_cast<uint32_t*>(dst)[0] = static_cast<uint32_t>(o);
+          reinterpret_cast<uint32_t*>(dst)[1] = static_cast<uint32_t>(static_cast<unsigned long long>(o) >> 32);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void load_src(const uint8_t* src, uint32_t code, bool* is_int,
+                                         long long* iv, double* fv, float* sv, bool* from_f64) {
+  *is_int = false; *from_f64 = false; *iv = 0; *fv = 0.0; *sv = 0.f;
+  switch (code) {
+    case DT_U8: case DT_BOOL: *is_int = true; *iv = *src; break;
+    case DT_I8: *is_int = true; *iv = *reinterpret_cast<const int8_t*>(src); break;
+    case DT_I16: *is_int = true; *iv = *reinterpret_cast<const int16_t*>(src); break;
+    case DT_I32: *is_int = true; *iv = *reinterpret_cast<const int32_t*>(src); break;
+    case DT_I64: *is_int = true; *iv = *reinterpret_cast<const long long*>(src); break;
+    case DT_F16: *sv = __half2float(*reinterpret_cast<const __half*>(src)); break;
+    case DT_BF16: *sv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(src)); break;
+    case DT_F32: *sv = *reinterpret_cast<const float*>(src); break;
+    case DT_F64: *from_f64 = true; *fv = *reinterpret_cast<const double*>(src); break;
+    default: break;
+  }
+}
+
+__global__ void __launch_bounds__(256) scatter_generic_kernel(const GenericParams p) {
+  extern __shared__ __align__(16) uint8_t gsm[];
+  const uint32_t R = p.rows_per_block;
+  const uint32_t spitch = p.row_pitch + 4;     // odd word count: conflict-free columns
+  unsigned long long* dptr = reinterpret_cast<unsigned long long*>(gsm);
+  uint8_t* stage = gsm + R * sizeof(unsigned long long);
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+
+  for (unsigned long long row0 = static_cast<unsigned long long>(blockIdx.x) * R; row0 < p.n_local;
+       row0 += static_cast<unsigned long long>(gridDim.x) * R) {
+    const uint32_t rows = static_cast<uint32_t>(min(static_cast<unsigned long long>(R), p.n_local - row0));
+    for (uint32_t r = threadIdx.x; r < rows; r += blockDim.x)
+      dptr[r] = dest_pointer(p.global_offset + row0 + r, p.key, p.plan, p.dst, p.row_pitch);
+    // zero the staging rows so padding bytes are deterministic
+    for (uint32_t w = threadIdx.x; w < rows * (spitch / 4); w += blockDim.x)
+      reinterpret_cast<uint32_t*>(stage)[w] = 0;
+    __syncthreads();
+    // phase 1: (field, row) work items; lanes run along rows => coalesced loads
+    const uint32_t work = p.num_fields * rows;
+    for (uint32_t idx = threadIdx.x; idx < work; idx += blockDim.x) {
+      const uint32_t fi = idx / rows;
+      const uint32_t r = idx - fi * rows;
+      const FieldDev f = p.fields[fi];
+      const uint32_t ss = rsdl_itemsize(f.src_code), ds = rsdl_itemsize(f.dst_code);
+      const uint8_t* src = f.src + (row0 + r) * static_cast<unsigned long long>(ss) * f.width;
+      uint8_t* out = stage + r * spitch + f.dst_off;
+      for (uint32_t w = 0; w < f.width; ++w) {
+        bool is_int, from_f64; long long iv; double fv; float sv;
+        load_src(src + w * ss, f.src_code, &is_int, &iv, &fv, &sv, &from_f64);
+        store_cast(out + w * ds, f.dst_code, is_int, iv, fv, sv, from_f64);
+      }
+    }
+    __syncthreads();
+    // phase 2: one warp per row, 128 B contiguous per store instruction
+    const uint32_t w_lo = p.write_lo / 4, w_hi = p.write_hi / 4;
+    for (uint32_t r = warp; r < rows; r += nwarps) {
+      uint32_t* drow = reinterpret_cast<uint32_t*>(dptr[r]);
+      const uint32_t* srow = reinterpret_cast<const uint32_t*>(stage + r * spitch);
+      for (uint32_t w = w_lo + lane; w < w_hi; w += 32) drow[w] = srow[w];
+    }
+    __syncthreads();
+  }
+  __threadfence_system();
+}
+
+// ---------------------------------------------------------------------------
+// K1 standalone: positions of local rows (tests, NCCL baseline)
+// ---------------------------------------------------------------------------
+__global__ void perm_positions_kernel(PermKeyDev key, PlanDev plan, unsigned long long global_offset,
+                                      unsigned long long n_local, int32_t* trainer, long long* slot) {
+  for (unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+       i < n_local; i += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
+    unsigned long long pos = rsdl_permute(global_offset + i, key);
+    uint32_t t; unsigned long long s;
+    rsdl_position_to_dest(pos, plan, &t, &s);
+    trainer[i] = static_cast<int32_t>(t);
+    slot[i] = static_cast<long long>(s);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K5 local row placement: dst[slots[i]] = rows[i] (NCCL baseline's last stage)
+// ---------------------------------------------------------------------------
+__global__ void place_rows_kernel(const uint8_t* rows, const long long* slots, unsigned long long n,
+                                  uint32_t pitch, uint8_t* dst) {
+  const int lane = threadIdx.x & 31;
+  const unsigned long long warp = (blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x) >> 5;
+  const unsigned long long nwarps = (static_cast<unsigned long long>(gridDim.x) * blockDim.x) >> 5;
+  const uint32_t vecs = pitch / 16;
+  for (unsigned long long i = warp; i < n; i += nwarps) {
+    const uint4* s = reinterpret_cast<const uint4*>(rows + i * pitch);
+    uint4* d = reinterpret_cast<uint4*>(dst + static_cast<unsigned long long>(slots[i]) * pitch);
+    for (uint32_t v = lane; v < vecs; v += 32) d[v] = s[v];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K13 key_checksum + batch reduction (consumer-side verification / bench sink)
+// ---------------------------------------------------------------------------
+__global__ void key_checksum_kernel(const uint8_t* packed, unsigned long long rows, uint32_t pitch,
+                                    uint32_t key_off, unsigned long long* out /*[2]: sum, xor*/) {
+  unsigned long long s = 0, x = 0;
+  for (unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+       i < rows; i += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
+    unsigned long long k = *reinterpret_cast<const unsigned long long*>(packed + i * pitch + key_off);
+    s += k;
+    // xor of a mixed key: order independent, sensitive to duplicates
+    unsigned long long z = k + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    x ^= z ^ (z >> 31);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    x ^= __shfl_xor_sync(0xffffffffu, x, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&out[0], s);
+    atomicXor(&out[1], x);
+  }
+}
+
+__global__ void batch_sum_f32_kernel(const uint8_t* packed, unsigned long long rows, uint32_t pitch,
+                                     uint32_t off, double* out) {
+  double s = 0.0;
+  for (unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+       i < rows; i += static_cast<unsigned long long>(gridDim.x) * blockDim.x)
+    s += static_cast<double>(*reinterpret_cast<const float*>(packed + i * pitch + off));
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+}
+
+// ---------------------------------------------------------------------------
+// K11 device ring signalling: epoch-tagged flags in (peer) HBM
+// ---------------------------------------------------------------------------
+__global__ void signal_flags_kernel(FlagTargets t, uint32_t value) {
+  if (threadIdx.x < t.count) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(t.ptr[threadIdx.x]), "r"(value) : "memory");
+  }
+}
+
+// Stream-side wait: spins (with back-off) until every flag >= value, or the
+// timeout expires, in which case *error is set instead of hanging the stream.
+__global__ void wait_flags_kernel(const uint32_t* flags, uint32_t count, uint32_t value,
+                                  unsigned long long timeout_ns, uint32_t* error) {
+  if (threadIdx.x >= count) return;
+  unsigned long long start;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(start));
+  uint32_t ns = 64;
+  while (true) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + threadIdx.x) : "memory");
+    if (static_cast<int32_t>(v - value) >= 0) break;
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    if (timeout_ns && now - start > timeout_ns) {
+      atomicExch(error, 1u + threadIdx.x);
+      break;
+    }
+    __nanosleep(ns);
+    if (ns < 4096) ns <<= 1;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Host launchers
+// ---------------------------------------------------------------------------
+template <int MODE>
+static void launch_fast_mode(const FastParams& p, int grid, cudaStream_t stream) {
+  const size_t smem = sizeof(FastSmem<MODE>) + 128;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(scatter_tma_kernel<MODE>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    configured = true;
+  }
+  scatter_tma_kernel<MODE><<<grid, kThreads, smem, stream>>>(p);
+}
+
+int fast_panel_cols(int mode) { return mode == 2 ? ModeTraits<2>::PANEL : ModeTraits<0>::PANEL; }
+int fast_tile_rows() { return kTileRows; }
+
+void launch_scatter_fast(const FastParams& p, int mode, int grid, cudaStream_t stream) {
+  if (p.n_local == 0) return;
+  switch (mode) {
+    case 0: launch_fast_mode<0>(p, grid, stream); break;
+    case 1: launch_fast_mode<1>(p, grid, stream); break;
+    case 2: launch_fast_mode<2>(p, grid, stream); break;
+    default: throw std::runtime_error("bad fast scatter mode");
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string("scatter_tma launch: ") + cudaGetErrorString(e));
+}
+
+void launch_scatter_generic(GenericParams p, int grid, cudaStream_t stream) {
+  if (p.n_local == 0) return;
+  const size_t budget = 160 * 1024;
+  uint32_t rows = static_cast<uint32_t>(budget / (p.row_pitch + 4 + sizeof(unsigned long long)));
+  rows = rows >= 256 ? 256 : (rows / 32) * 32;
+  if (rows == 0) throw std::runtime_error("row pitch too large for the generic scatter kernel");
+  p.rows_per_block = rows;
+  const size_t smem = static_cast<size_t>(rows) * (p.row_pitch + 4 + sizeof(unsigned long long)) + 16;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(scatter_generic_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(budget + 4096));
+    if (e != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    configured = budget + 4096;
+  }
+  scatter_generic_kernel<<<grid, 256, smem, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string("scatter_generic launch: ") + cudaGetErrorString(e));
+}
+
+static void check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+void launch_perm_positions(const PermKeyDev& key, const PlanDev& plan, unsigned long long global_offset,
+                           unsigned long long n_local, int32_t* trainer, long long* slot,
+                           cudaStream_t stream) {
+  if (n_local == 0) return;
+  int grid = static_cast<int>(std::min<unsigned long long>((n_local + 255) / 256, 148 * 8));
+  perm_positions_kernel<<<grid, 256, 0, stream>>>(key, plan, global_offset, n_local, trainer, slot);
+  check_launch("perm_positions");
+}
+
+void launch_place_rows(const uint8_t* rows, const long long* slots, unsigned long long n,
+                       uint32_t pitch, uint8_t* dst, cudaStream_t stream) {
+  if (n == 0) return;
+  int grid = static_cast<int>(std::min<unsigned long long>((n + 7) / 8, 148 * 8));
+  place_rows_kernel<<<grid, 256, 0, stream>>>(rows, slots, n, pitch, dst);
+  check_launch("place_rows");
+}
+
+void launch_key_checksum(const uint8_t* packed, unsigned long long rows, uint32_t pitch,
+                         uint32_t key_off, unsigned long long* out, cudaStream_t stream) {
+  if (rows == 0) return;
+  int grid = static_cast<int>(std::min<unsigned long long>((rows + 255) / 256, 148 * 4));
+  key_checksum_kernel<<<grid, 256, 0, stream>>>(packed, rows, pitch, key_off, out);
+  check_launch("key_checksum");
+}
+
+void launch_batch_sum_f32(const uint8_t* packed, unsigned long long rows, uint32_t pitch,
+                          uint32_t off, double* out, cudaStream_t stream) {
+  if (rows == 0) return;
+  int grid = static_cast<int>(std::min<unsigned long long>((rows + 255) / 256, 148 * 4));
+  batch_sum_f32_kernel<<<grid, 256, 0, stream>>>(packed, rows, pitch, off, out);
+  check_launch("batch_sum_f32");
+}
+
+void launch_signal_flags(const FlagTargets& t, uint32_t value, cudaStream_t stream) {
+  if (t.count == 0) return;
+  signal_flags_kernel<<<1, RSDL_MAX_TRAINERS, 0, stream>>>(t, value);
+  check_launch("signal_flags");
+}
+
+void launch_wait_flags(const uint32_t* flags, uint32_t count, uint32_t value,
+                       unsigned long long timeout_ns, uint32_t* error, cudaStream_t stream) {
+  if (count == 0) return;
+  wait_flags_kernel<<<1, RSDL_MAX_TRAINERS, 0, stream>>>(flags, count, value, timeout_ns, error);
+  check_launch("wait_flags");
+}
+
+}  // namespace rsdl

@@ -95,7 +95,7 @@ def pack_fp8_block_scaled(columns: Dict[str, np.ndarray], layout,
     pad = nblk * BLOCK - nelem
     xp = np.pad(x, ((0, 0), (0, pad))) if pad else x
     blocks = xp.reshape(n, nblk, BLOCK)
-    amax = np.abs(blocks).max(axis=2)
+    amax = np.fmax.reduce(np.abs(blocks), axis=2)      # NaNs never win (device rule)
     amax = np.where(np.isnan(amax), 0.0, amax)
     e = block_scale_exponent(amax)                # [n, nblk]
     scaled = blocks.astype(np.float64) * np.exp2(-e.astype(np.float64))[:, :, None]

@@ -174,8 +174,9 @@ def build_layout(columns: Sequence[Tuple[str, int, int, int]],
     scale_offset = -1
     if fp8_block_scale:
         nelem = sum(f.width for f in fields if f.dst_code == DT_FP8)
-        scale_offset = off
-        off += (nelem + 31) // 32
+        # 16-aligned so the kernel's 16-byte payload stores never touch a scale
+        scale_offset = _align(off, 16)
+        off = scale_offset + (nelem + 31) // 32
     return RowLayout(tuple(fields), max(16, _align(off, 16)), scale_offset)
 
 

@@ -1,0 +1,628 @@
+"""CUDA shuffle engine: HBM-resident columnar table, epoch ring, P2P scatter.
+
+One instance per process (= per GPU). It replaces, for the GPU path, everything
+the reference runs as Ray tasks per epoch (``shuffle_map``/``shuffle_reduce``,
+reference ``shuffle.py:129-200``) and everything Ray's object store does for it:
+
+* **ingest** - the rows this rank owns are decoded once (``runtime/ingest.py``)
+  into *pinned* host buffers and staged into HBM with ``cudaMemcpyAsync`` on a
+  copy stream (kernel-table rows K9/K10). ``resident="hbm"`` keeps the columnar
+  table on the device for every epoch; ``resident="host"`` keeps it in pinned
+  memory and re-streams it chunk by chunk each epoch (double-buffered H2D that
+  overlaps the scatter kernel) for datasets that do not fit.
+* **epoch ring** (K11) - ``max_concurrent_epochs`` destination slots per local
+  trainer inside one ``cudaMalloc`` arena that is exported with CUDA IPC and
+  mapped by every peer, plus epoch-tagged signal words in the same arena:
+  ``produced[slot][src_rank]`` (written by each source after its scatter kernel)
+  and ``consumed[trainer]`` (written on the trainer's stream when it has finished
+  an epoch - the device analogue of ``task_done`` + ``queue.join()``).
+* **exchange** - one fused kernel launch per (epoch, source chunk) pushes every
+  row to its final ``(trainer, slot)`` in local or peer HBM
+  (``csrc/shuffle_kernels.cu``); ``exchange="nccl"`` swaps in the NCCL
+  ``all_to_all_single`` baseline (``parallel/nccl_baseline.py``).
+
+Every wait on a flag has a timeout and raises a clear error instead of hanging
+(the reference deadlocks on a dead trainer).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+import timeit
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from ray_shuffling_data_loader_b200.ops import layout as L
+from ray_shuffling_data_loader_b200.ops import perm
+from ray_shuffling_data_loader_b200.ops.plan import ShufflePlan
+from ray_shuffling_data_loader_b200.parallel import bootstrap
+from ray_shuffling_data_loader_b200.runtime import ingest
+from ray_shuffling_data_loader_b200.runtime.chunks import EpochBuffer
+from ray_shuffling_data_loader_b200 import stats as stats_mod
+
+
+def load_native():
+    """Import the sm_100a extension; on a GPU box a missing build is fatal
+    (never fall back silently to a slow path)."""
+    try:
+        from ray_shuffling_data_loader_b200 import _C
+        return _C
+    except ImportError as e:
+        raise RuntimeError(
+            "the native extension ray_shuffling_data_loader_b200._C is not built; "
+            "run `python -m ray_shuffling_data_loader_b200._build`") from e
+
+
+_ROW_PAD = 256          # source columns are padded to this many rows (TMA tiles)
+_ALIGN = 256
+_FIELD_DTYPE = np.dtype([("src", "<u8"), ("src_code", "<u4"), ("dst_code", "<u4"),
+                         ("dst_off", "<u4"), ("width", "<u4")])
+
+
+def _align(x: int, a: int = _ALIGN) -> int:
+    return (x + a - 1) // a * a
+
+
+class _CudaView:
+    """Minimal ``__cuda_array_interface__`` carrier for zero-copy torch views."""
+
+    def __init__(self, ptr: int, shape: Tuple[int, ...], typestr: str = "|u1"):
+        self.__cuda_array_interface__ = {
+            "shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+            "version": 3, "strides": None}
+
+
+def as_torch(ptr: int, shape: Tuple[int, ...], device_index: int, typestr: str = "|u1"):
+    import torch
+    if int(np.prod(shape)) == 0:
+        dt = {"|u1": torch.uint8, "<i4": torch.int32, "<i8": torch.int64,
+              "<u4": torch.int32}[typestr]
+        return torch.empty(shape, dtype=dt, device=f"cuda:{device_index}")
+    return torch.as_tensor(_CudaView(ptr, shape, typestr), device=f"cuda:{device_index}")
+
+
+def pinned_array(C, shape, dtype) -> Tuple[np.ndarray, int]:
+    """numpy array over freshly allocated pinned host memory -> (array, ptr)."""
+    dtype = np.dtype(dtype)
+    nbytes = max(1, int(np.prod(shape)) * dtype.itemsize)
+    ptr = C.pinned_alloc(nbytes)
+    raw = np.ctypeslib.as_array((ctypes.c_uint8 * nbytes).from_address(ptr))
+    arr = raw[:int(np.prod(shape)) * dtype.itemsize].view(dtype).reshape(shape)
+    return arr, ptr
+
+
+class DeviceShuffleEngine:
+    device = "cuda"
+
+    def __init__(self, filenames: Sequence[str], plan_args: dict, layout_fn,
+                 seed: int, rank: int = 0, world: int = 1, stats_collector=None,
+                 max_concurrent_epochs: int = 2, num_threads: Optional[int] = None,
+                 resident: str = "hbm", stream_chunk_rows: Optional[int] = None,
+                 exchange: str = "p2p", wait_mode: str = "host",
+                 flag_timeout_s: float = 300.0, index=None,
+                 device_index: Optional[int] = None, grid: Optional[int] = None,
+                 process_group=None, force_generic: bool = False):
+        import torch
+        self.C = load_native()
+        self.torch = torch
+        if device_index is None:
+            device_index = torch.cuda.current_device()
+        self.device_index = device_index
+        torch.cuda.set_device(device_index)
+        self.C.set_device(device_index)
+        cc = self.C.compute_capability(device_index)
+        if cc[0] < 10:
+            raise RuntimeError(f"sm_100a kernels need a Blackwell GPU, found sm_{cc[0]}{cc[1]}")
+        self.index = index or ingest.scan_files(filenames)
+        self.plan = ShufflePlan(num_rows=self.index.num_rows, **plan_args)
+        if world > 1 and self.plan.num_trainers != world:
+            raise ValueError("distributed mode needs num_trainers == world size")
+        if self.plan.num_trainers > self.C.MAX_TRAINERS:
+            raise ValueError(f"at most {self.C.MAX_TRAINERS} trainers are supported")
+        self.layout: L.RowLayout = layout_fn(self.index.schema)
+        self.seed = int(seed)
+        self.rank, self.world, self.pg = rank, world, process_group
+        self.stats = stats_collector
+        self.window = max(1, int(max_concurrent_epochs))
+        self.num_threads = num_threads or max(1, min(16, (os.cpu_count() or 2)))
+        if resident not in ("hbm", "host"):
+            raise ValueError("resident must be 'hbm' or 'host'")
+        if exchange not in ("p2p", "nccl"):
+            raise ValueError("exchange must be 'p2p' or 'nccl'")
+        if wait_mode not in ("host", "stream"):
+            raise ValueError("wait_mode must be 'host' or 'stream'")
+        self.resident, self.exchange, self.wait_mode = resident, exchange, wait_mode
+        self.flag_timeout_s = flag_timeout_s
+        self.force_generic = force_generic
+        self.local_trainers: List[int] = ([rank] if world > 1
+                                          else list(range(self.plan.num_trainers)))
+        self.sm_count = self.C.sm_count(device_index)
+        self.grid_override = grid
+        self.launches = 0                 # kernels launched by this engine
+        self._lock = threading.Lock()
+        self._closed = False
+        self._ingested = False
+        self._events: Dict[int, Tuple[int, int]] = {}
+        self._epoch_kernel_ms: Dict[int, float] = {}
+
+        lo, hi = self.plan.source_range(rank, world)
+        self.src_lo, self.n_local = lo, hi - lo
+        self.chunk_rows = (self.n_local if resident == "hbm" else
+                           max(1, min(self.n_local or 1,
+                                      stream_chunk_rows or self.plan.batch_size)))
+        if resident == "host":
+            self.chunk_rows = _align(self.chunk_rows, self.C.TILE_ROWS)
+
+        prio_lo, prio_hi = self.C.stream_priority_range()
+        # The shuffle must not starve training kernels: lowest priority stream.
+        self.shuffle_stream = self.C.stream_create(prio_lo)
+        self.copy_stream = self.C.stream_create(prio_lo)
+        self.poller = self.C.FlagPoller()
+        self.host_pool = self.C.HostPool(self.num_threads)
+        self._alloc_dest_arena()
+        self._setup_sources()
+        self._bytes_fn = self.bytes_in_use
+        stats_mod.register_bytes_used_source(self._bytes_fn)
+
+    # ------------------------------------------------------------------
+    # memory
+    # ------------------------------------------------------------------
+    def _alloc_dest_arena(self):
+        C, plan = self.C, self.plan
+        T = plan.num_trainers
+        self.slot_rows = plan.max_trainer_rows
+        self.slot_bytes = _align(max(1, self.slot_rows) * self.layout.row_pitch)
+        nloc = len(self.local_trainers)
+        # header: produced[W][world] | consumed[T] | error[4]  (uint32 words)
+        self.off_produced = 0
+        self.off_consumed = _align(self.window * self.world * 4, 128)
+        self.off_error = self.off_consumed + _align(T * 4, 128)
+        self.header_bytes = _align(self.off_error + 16, 4096)
+        self.arena_bytes = self.header_bytes + self.window * nloc * self.slot_bytes
+        self.arena = C.device_malloc(self.arena_bytes)
+        # Zero once: flags start at 0 and row padding stays deterministic.
+        C.device_memset_async(self.arena, 0, self.arena_bytes, self.shuffle_stream)
+        C.stream_synchronize(self.shuffle_stream)
+        # peer mapping (CUDA IPC) - rank r's arena base as seen from this process
+        self.peer_base: List[int] = [self.arena] * self.world
+        self._opened: List[int] = []
+        if self.world > 1:
+            handle = C.ipc_get_handle(self.arena)
+            handles = bootstrap.all_gather_object(
+                (self.rank, self.device_index, handle, self.arena_bytes), group=self.pg)
+            for r, dev, h, nbytes in handles:
+                if r == self.rank:
+                    continue
+                if nbytes != self.arena_bytes:
+                    raise RuntimeError("ranks disagree on the arena size")
+                base = C.ipc_open_handle(h)
+                self._opened.append(base)
+                self.peer_base[r] = base
+            bootstrap.barrier(self.pg)
+
+    def _owner(self, trainer: int) -> Tuple[int, int]:
+        """(owning rank, index among that rank's local trainers)."""
+        return (trainer, 0) if self.world > 1 else (0, trainer)
+
+    def _slot_ptr(self, slot: int, trainer: int) -> int:
+        owner, j = self._owner(trainer)
+        nloc = 1 if self.world > 1 else self.plan.num_trainers
+        return (self.peer_base[owner] + self.header_bytes
+                + (slot * nloc + j) * self.slot_bytes)
+
+    def _produced_ptr(self, on_rank: int, slot: int, src_rank: int) -> int:
+        return self.peer_base[on_rank] + self.off_produced + (slot * self.world + src_rank) * 4
+
+    def _consumed_ptr(self, on_rank: int, trainer: int) -> int:
+        return self.peer_base[on_rank] + self.off_consumed + trainer * 4
+
+    def _setup_sources(self):
+        """Device storage for the source columns (whole table or 2 staging
+        chunks) and the per-buffer column-pointer / field-descriptor arrays."""
+        C, lay = self.C, self.layout
+        self.src_fields = list(lay.fields)
+        rows_buf = _align(max(1, self.chunk_rows), _ROW_PAD)
+        self.col_bytes = [_align(rows_buf * L.itemsize(f.src_code) * f.width)
+                          for f in self.src_fields]
+        self.num_src_bufs = 1 if self.resident == "hbm" else 2
+        per_buf = sum(self.col_bytes)
+        self.src_arena_bytes = per_buf * self.num_src_bufs + 4096
+        self.src_arena = C.device_malloc(self.src_arena_bytes)
+        self.src_col_ptrs: List[List[int]] = []
+        for b in range(self.num_src_bufs):
+            ptrs, off = [], self.src_arena + b * per_buf
+            for nb in self.col_bytes:
+                ptrs.append(off)
+                off += nb
+            self.src_col_ptrs.append(ptrs)
+        self._plan_kernels()
+        # descriptor tables live in a small device buffer, uploaded once
+        tables = []
+        for b in range(self.num_src_bufs):
+            ptrs = self.src_col_ptrs[b]
+            fast_cols = np.array([ptrs[i] for i in self.fast_field_idx], dtype=np.uint64)
+            gen = np.zeros(len(self.generic_field_idx), dtype=_FIELD_DTYPE)
+            for k, i in enumerate(self.generic_field_idx):
+                f = self.src_fields[i]
+                gen[k] = (ptrs[i], f.src_code, f.dst_code, f.offset, f.width)
+            tables.append((fast_cols, gen))
+        blob = b"".join(_pad(a.tobytes()) + _pad(g.tobytes()) for a, g in tables)
+        self.desc_arena = C.device_malloc(max(256, len(blob)))
+        self._desc_host, self._desc_host_ptr = pinned_array(C, (max(256, len(blob)),), np.uint8)
+        self._desc_host[:len(blob)] = np.frombuffer(blob, dtype=np.uint8)
+        C.memcpy_async(self.desc_arena, self._desc_host_ptr, len(blob), C.H2D, self.shuffle_stream)
+        C.stream_synchronize(self.shuffle_stream)
+        self.fast_cols_dev, self.generic_fields_dev = [], []
+        off = self.desc_arena
+        for a, g in tables:
+            self.fast_cols_dev.append(off)
+            off += len(_pad(a.tobytes()))
+            self.generic_fields_dev.append(off)
+            off += len(_pad(g.tobytes()))
+        if self.resident == "host":
+            self.h2d_done = [C.event_create(False) for _ in range(self.num_src_bufs)]
+            self.buf_free = [C.event_create(False) for _ in range(self.num_src_bufs)]
+            self._buf_used = [False] * self.num_src_bufs
+
+    def _plan_kernels(self):
+        """Split the layout's fields between the TMA fast kernel and the generic
+        kernel (see csrc/shuffle_kernels.cu)."""
+        lay = self.layout
+        fields = self.src_fields
+        self.fast_mode = -1
+        self.fast_field_idx: List[int] = []
+        self.generic_field_idx = list(range(len(fields)))
+        self.generic_range = (0, lay.row_pitch)
+        if self.force_generic or not fields:
+            return
+        # longest prefix that is dense from 0, width 1, one 4-byte source dtype,
+        # one destination dtype that the fast kernel can emit
+        first = fields[0]
+        if first.width != 1 or L.itemsize(first.src_code) != 4 or first.offset != 0:
+            return
+        if first.dst_code == first.src_code:
+            mode = 0
+        elif first.src_code == L.DT_F32 and first.dst_code == L.DT_BF16:
+            mode = 1
+        elif (first.src_code == L.DT_F32 and first.dst_code == L.DT_FP8
+              and lay.scale_offset >= 0):
+            mode = 2
+        else:
+            return
+        n, off = 0, 0
+        dsz = L.itemsize(first.dst_code)
+        for f in fields:
+            if (f.width != 1 or f.src_code != first.src_code
+                    or f.dst_code != first.dst_code or f.offset != off):
+                break
+            n += 1
+            off += dsz
+        rest = list(range(n, len(fields)))
+        if rest:
+            # The fast kernel writes whole 16-byte groups (and, in fp8 mode, the
+            # scale bytes); the remainder must start past them.
+            fast_end = _align(off, 16)
+            rest_lo = min(fields[i].offset for i in rest) // 4 * 4
+            scale_lo = lay.scale_offset if mode == 2 else lay.row_pitch
+            rest_hi = _align(max(fields[i].offset + fields[i].dst_bytes for i in rest), 4)
+            if rest_lo < fast_end or (mode == 2 and rest_hi > scale_lo):
+                return
+            self.generic_range = (rest_lo, rest_hi)
+        if n < 4:
+            return      # not worth a TMA launch
+        self.fast_mode = mode
+        self.fast_field_idx = list(range(n))
+        self.generic_field_idx = rest
+
+    # ------------------------------------------------------------------
+    # ingest
+    # ------------------------------------------------------------------
+    def _ensure_ingested(self, epoch: int):
+        with self._lock:
+            if self._ingested:
+                if self.stats is not None:
+                    for _ in range(len(self.index.filenames)):
+                        self.stats.map_start(epoch)
+                        self.stats.map_done(epoch, 0.0, 0.0)
+                return
+            C = self.C
+            t0 = timeit.default_timer()
+            nfiles = len(self.index.filenames)
+            if self.stats is not None:
+                for _ in range(nfiles):
+                    self.stats.map_start(epoch)
+            self._pinned: List[int] = []
+
+            def alloc(shape, dt):
+                arr, ptr = pinned_array(C, shape, dt)
+                self._pinned.append(ptr)
+                return arr
+
+            names = [f.name for f in self.src_fields]
+            table = ingest.load_table(self.index, self.src_lo, self.src_lo + self.n_local,
+                                      columns=list(dict.fromkeys(names)),
+                                      num_threads=self.num_threads, alloc=alloc)
+            self.host_table = table
+            self.host_cols = [table.columns[f.name] for f in self.src_fields]
+            for f, col in zip(self.src_fields, self.host_cols):
+                want = np.dtype(L.numpy_storage_dtype(f.src_code))
+                if col.dtype != want:
+                    raise TypeError(f"column {f.name}: decoded {col.dtype}, expected {want}")
+            if self.resident == "hbm":
+                for ptr, col in zip(self.src_col_ptrs[0], self.host_cols):
+                    if col.nbytes:
+                        C.memcpy_async(ptr, col.ctypes.data, col.nbytes, C.H2D, self.copy_stream)
+                C.stream_synchronize(self.copy_stream)
+                # decoded host copy is no longer needed once resident in HBM
+                self.host_cols = None
+                self.host_table = None
+                for ptr in self._pinned:
+                    C.pinned_free(ptr)
+                self._pinned = []
+            self._ingested = True
+            dur = timeit.default_timer() - t0
+            self.ingest_seconds = dur
+            reads = table.read_durations or [0.0]
+            if self.stats is not None:
+                for _ in range(nfiles):
+                    self.stats.map_done(epoch, dur / nfiles, float(np.mean(reads)))
+
+    # ------------------------------------------------------------------
+    # one epoch
+    # ------------------------------------------------------------------
+    def _grid(self, work_items: int) -> int:
+        g = self.grid_override or self.sm_count
+        return max(1, min(g, work_items))
+
+    def _launch_chunk(self, key_words, buf: int, n_rows: int, global_offset: int,
+                      dst: List[int]):
+        C, lay, plan = self.C, self.layout, self.plan
+        if n_rows <= 0:
+            return
+        if self.fast_mode >= 0:
+            ncols = len(self.fast_field_idx)
+            panels = -(-ncols // C.fast_panel_cols(self.fast_mode))
+            tiles = -(-n_rows // C.TILE_ROWS)
+            C.scatter_fast(key=key_words, num_rows=plan.num_rows,
+                           num_trainers=plan.num_trainers, cols=self.fast_cols_dev[buf],
+                           num_cols=ncols, n_local=n_rows, global_offset=global_offset,
+                           row_pitch=lay.row_pitch,
+                           scale_offset=max(0, lay.scale_offset), dst=dst,
+                           mode=self.fast_mode, grid=self._grid(tiles * panels),
+                           stream=self.shuffle_stream)
+            self.launches += 1
+        if self.generic_field_idx:
+            lo, hi = self.generic_range
+            C.scatter_generic(key=key_words, num_rows=plan.num_rows,
+                              num_trainers=plan.num_trainers,
+                              fields=self.generic_fields_dev[buf],
+                              num_fields=len(self.generic_field_idx), n_local=n_rows,
+                              global_offset=global_offset, row_pitch=lay.row_pitch,
+                              write_lo=lo, write_hi=hi, dst=dst,
+                              grid=max(1, min(self.sm_count * 2, -(-n_rows // 64))),
+                              stream=self.shuffle_stream)
+            self.launches += 1
+
+    def start_epoch(self, epoch: int) -> Dict[int, EpochBuffer]:
+        """Enqueue the epoch's shuffle on the side stream (non-blocking apart
+        from cross-rank back-pressure) and return the destination buffers."""
+        if self._closed:
+            raise RuntimeError("engine is closed")
+        C, plan = self.C, self.plan
+        C.set_device(self.device_index)      # driver thread: device is per-thread
+        self.torch.cuda.set_device(self.device_index)
+        self._ensure_ingested(epoch)
+        slot = epoch % self.window
+        if epoch >= self.window:
+            # Back-pressure: every trainer must have released this slot's
+            # previous epoch before any source may overwrite it.
+            lag = self.poller.wait(self._consumed_ptr(self.rank, 0), plan.num_trainers,
+                                   epoch - self.window + 1, self.flag_timeout_s)
+            if lag >= 0:
+                raise TimeoutError(
+                    f"trainer {lag} did not release epoch {epoch - self.window} within "
+                    f"{self.flag_timeout_s}s (stalled or dead consumer)")
+        t_start = timeit.default_timer()
+        if self.stats is not None:
+            for _ in range(plan.num_reducers):
+                self.stats.reduce_start(epoch)
+        key_words = list(perm.make_key(plan.num_rows, self.seed, epoch).as_words())
+        dst = [self._slot_ptr(slot, t) for t in range(plan.num_trainers)]
+        ev0, ev1 = C.event_create(True), C.event_create(True)
+        C.event_record(ev0, self.shuffle_stream)
+        if self.exchange == "nccl":
+            from ray_shuffling_data_loader_b200.parallel import nccl_baseline
+            nccl_baseline.exchange_epoch(self, key_words, slot)
+        elif self.resident == "hbm":
+            self._launch_chunk(key_words, 0, self.n_local, self.src_lo, dst)
+        else:
+            self._stream_epoch(key_words, dst)
+        C.event_record(ev1, self.shuffle_stream)
+        # publish: produced[slot][rank] = epoch + 1 on every rank
+        targets = [self._produced_ptr(r, slot, self.rank) for r in range(self.world)]
+        C.signal_flags(targets, epoch + 1, self.shuffle_stream)
+        self.launches += 1
+        self._events[epoch] = (ev0, ev1)
+
+        buffers = {}
+        for t in self.local_trainers:
+            rows = plan.trainer_rows(t)
+            data = as_torch(self._slot_ptr(slot, t), (rows, self.layout.row_pitch),
+                            self.device_index)
+            buffers[t] = EpochBuffer(
+                epoch, t, rows, self.layout, data, "cuda",
+                wait_fn=self._make_wait(epoch, slot, t_start),
+                release_fn=self._make_release(epoch, t))
+        return buffers
+
+    def _stream_epoch(self, key_words, dst):
+        """resident='host': double-buffered H2D of source chunks overlapping the
+        scatter kernel of the previous chunk."""
+        C = self.C
+        k = 0
+        for row0 in range(0, self.n_local, self.chunk_rows):
+            rows = min(self.chunk_rows, self.n_local - row0)
+            b = k % self.num_src_bufs
+            if self._buf_used[b]:
+                C.stream_wait_event(self.copy_stream, self.buf_free[b])
+            for f, ptr, col in zip(self.src_fields, self.src_col_ptrs[b], self.host_cols):
+                part = col[row0:row0 + rows]
+                C.memcpy_async(ptr, part.ctypes.data, part.nbytes, C.H2D, self.copy_stream)
+            C.event_record(self.h2d_done[b], self.copy_stream)
+            C.stream_wait_event(self.shuffle_stream, self.h2d_done[b])
+            self._launch_chunk(key_words, b, rows, self.src_lo + row0, dst)
+            C.event_record(self.buf_free[b], self.shuffle_stream)
+            self._buf_used[b] = True
+            k += 1
+
+    def h2d_bytes_per_epoch(self) -> int:
+        if self.resident != "host":
+            return 0
+        return int(sum(self.n_local * L.itemsize(f.src_code) * f.width
+                       for f in self.src_fields))
+
+    def _make_wait(self, epoch: int, slot: int, t_start: float):
+        state = {"done": False}
+
+        def wait(timeout: Optional[float] = None):
+            if state["done"]:
+                return
+            self.C.set_device(self.device_index)
+            if self.wait_mode == "stream":
+                # Device-side wait on the consumer's stream: no host sync.
+                stream = self.torch.cuda.current_stream().cuda_stream
+                self.C.wait_flags(self._produced_ptr(self.rank, slot, 0), self.world,
+                                  epoch + 1, int(self.flag_timeout_s * 1e9),
+                                  self.arena + self.off_error, stream)
+                self.launches += 1
+            else:
+                limit = self.flag_timeout_s if timeout is None else timeout
+                lag = self.poller.wait(self._produced_ptr(self.rank, slot, 0), self.world,
+                                       epoch + 1, limit)
+                if lag >= 0:
+                    raise TimeoutError(
+                        f"source rank {lag} did not deliver epoch {epoch} within {limit}s")
+            state["done"] = True
+            self._epoch_done_stats(epoch, t_start)
+        return wait
+
+    def _epoch_done_stats(self, epoch: int, t_start: float):
+        ev = self._events.pop(epoch, None)
+        if ev is None:
+            return
+        ms = None
+        try:
+            if self.C.event_query(ev[1]):
+                ms = self.C.event_elapsed_ms(ev[0], ev[1])
+        except Exception:
+            ms = None
+        self.C.event_destroy(ev[0])
+        self.C.event_destroy(ev[1])
+        if ms is not None:
+            self._epoch_kernel_ms[epoch] = ms
+        if self.stats is not None:
+            dur = (ms / 1e3) if ms is not None else (timeit.default_timer() - t_start)
+            R = self.plan.num_reducers
+            for _ in range(R):
+                self.stats.reduce_done(epoch, dur / R)
+            if ms is not None:
+                remote = self.n_local * self.layout.row_pitch * (self.world - 1) // max(1, self.world)
+                self.stats.exchange_done(epoch, remote, ms / 1e3)
+
+    def epoch_kernel_ms(self, epoch: int) -> Optional[float]:
+        return self._epoch_kernel_ms.get(epoch)
+
+    def _make_release(self, epoch: int, trainer: int):
+        def release():
+            if self._closed:
+                return
+            self.C.set_device(self.device_index)
+            # Stream-ordered after everything the trainer enqueued on its stream.
+            stream = self.torch.cuda.current_stream().cuda_stream
+            targets = [self._consumed_ptr(r, trainer) for r in range(self.world)]
+            self.C.signal_flags(targets, epoch + 1, stream)
+            self.launches += 1
+        return release
+
+    def release_epoch(self, epoch, buffers):
+        for b in buffers.values():
+            b.release()
+
+    # ------------------------------------------------------------------
+    # helpers used by tests / bench
+    # ------------------------------------------------------------------
+    def check_error(self):
+        err = self.poller.read(self.arena + self.off_error, 1)[0]
+        if err:
+            raise TimeoutError(f"device-side flag wait timed out (flag {err - 1})")
+
+    def key_checksum(self, packed, field_name: str = "key") -> Tuple[int, int]:
+        """Order-independent (sum, xor-hash) of an int64 field of packed rows."""
+        torch = self.torch
+        f = self.layout.field(field_name)
+        out = torch.zeros(2, dtype=torch.int64, device=packed.device)
+        self.C.key_checksum(packed.data_ptr(), packed.shape[0], self.layout.row_pitch,
+                            f.offset, out.data_ptr(),
+                            torch.cuda.current_stream().cuda_stream)
+        self.launches += 1
+        s, x = out.cpu().tolist()
+        return s & (2**64 - 1), x & (2**64 - 1)
+
+    def batch_sum(self, packed, field_name: str, out=None):
+        """Device-side fp64 sum of an fp32 field of a packed batch (bench sink)."""
+        torch = self.torch
+        f = self.layout.field(field_name)
+        if out is None:
+            out = torch.zeros(1, dtype=torch.float64, device=packed.device)
+        self.C.batch_sum_f32(packed.data_ptr(), packed.shape[0], self.layout.row_pitch,
+                             f.offset, out.data_ptr(),
+                             torch.cuda.current_stream().cuda_stream)
+        self.launches += 1
+        return out
+
+    def bytes_in_use(self) -> int:
+        if self._closed:
+            return 0
+        return int(self.arena_bytes + self.src_arena_bytes)
+
+    def close(self):
+        if self._closed:
+            return
+        self._closed = True
+        stats_mod.unregister_bytes_used_source(self._bytes_fn)
+        C = self.C
+        try:
+            C.stream_synchronize(self.shuffle_stream)
+            C.stream_synchronize(self.copy_stream)
+            self.torch.cuda.synchronize(self.device_index)
+            if self.world > 1:
+                # nobody may unmap/free while a peer can still push into us
+                bootstrap.barrier(self.pg)
+        finally:
+            for base in self._opened:
+                try:
+                    C.ipc_close_handle(base)
+                except Exception:
+                    pass
+            for ev in self._events.values():
+                C.event_destroy(ev[0])
+                C.event_destroy(ev[1])
+            self._events.clear()
+            if self.resident == "host":
+                for e in self.h2d_done + self.buf_free:
+                    C.event_destroy(e)
+            for ptr in getattr(self, "_pinned", []):
+                C.pinned_free(ptr)
+            self._pinned = []
+            C.pinned_free(self._desc_host_ptr)
+            C.device_free(self.desc_arena)
+            C.device_free(self.src_arena)
+            C.device_free(self.arena)
+            C.stream_destroy(self.shuffle_stream)
+            C.stream_destroy(self.copy_stream)
+
+
+def _pad(b: bytes, a: int = 256) -> bytes:
+    return b + b"\0" * ((-len(b)) % a) if b else b"\0" * a

@@ -1,0 +1,200 @@
+"""GPU tests (run under gpurun): every CUDA kernel is diffed byte for byte
+against the numpy golden engine (implication 3)."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device")]
+
+from ray_shuffling_data_loader_b200.ops import layout as L
+from ray_shuffling_data_loader_b200.ops import perm
+from ray_shuffling_data_loader_b200.ops.plan import ShufflePlan
+
+
+def _native():
+    from ray_shuffling_data_loader_b200.runtime.device_engine import load_native
+    return load_native()
+
+
+def _engines(filenames, layout_fn, num_trainers, seed=5, batch_size=512, **dev_opts):
+    from ray_shuffling_data_loader_b200.runtime.cpu_engine import CpuShuffleEngine
+    from ray_shuffling_data_loader_b200.runtime.device_engine import DeviceShuffleEngine
+    plan_args = dict(num_trainers=num_trainers, num_reducers=max(2, num_trainers),
+                     batch_size=batch_size, drop_last=False)
+    cpu = CpuShuffleEngine(filenames, plan_args, layout_fn, seed)
+    dev = DeviceShuffleEngine(filenames, plan_args, layout_fn, seed, **dev_opts)
+    return cpu, dev
+
+
+def _compare_epochs(cpu, dev, epochs=(0, 1, 2), fields_only=False):
+    for epoch in epochs:
+        cb = cpu.start_epoch(epoch)
+        db = dev.start_epoch(epoch)
+        for t in dev.local_trainers:
+            cb[t].wait(60)
+            db[t].wait(60)
+            got = db[t].data.cpu().numpy()
+            want = cb[t].data
+            assert got.shape == want.shape
+            if fields_only:
+                for f in dev.layout.fields:
+                    assert np.array_equal(L.unpack_field(got, f), L.unpack_field(want, f)), \
+                        (epoch, t, f.name)
+            else:
+                assert np.array_equal(got, want), (epoch, t)
+        for t in dev.local_trainers:
+            db[t].release()
+    torch.cuda.synchronize()
+
+
+def _float_files(tmp_path_factory, ncols, nrows=20_011, nfiles=3, name="f"):
+    from ray_shuffling_data_loader_b200.data_generation import generate_data, float_spec
+    d = tmp_path_factory.mktemp(f"{name}{ncols}")
+    files, _ = generate_data(nrows, nfiles, 2, 0.0, str(d),
+                             data_spec=float_spec(ncols, np.float32), seed=ncols)
+    return files
+
+
+def _f32_layout(cols, dst=L.DT_F32, fp8=False):
+    def fn(schema):
+        return L.build_layout([(c, schema[c][0], dst, 1) for c in cols], fp8_block_scale=fp8)
+    return fn
+
+
+def test_perm_positions_matches_numpy():
+    C = _native()
+    for n, T, off, cnt in [(1000, 1, 0, 1000), (100_003, 8, 12_345, 40_000),
+                           (7, 3, 0, 7), (1 << 20, 5, 999, 5000)]:
+        for epoch in (0, 3):
+            key = perm.make_key(n, 77, epoch)
+            plan = ShufflePlan(n, T, T, 10)
+            tr = torch.empty(cnt, dtype=torch.int32, device="cuda")
+            sl = torch.empty(cnt, dtype=torch.int64, device="cuda")
+            C.perm_positions(list(key.as_words()), n, T, off, cnt, tr.data_ptr(),
+                             sl.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            pos = perm.permute(np.arange(off, off + cnt, dtype=np.uint64), key)
+            t_ref, s_ref = plan.position_to_trainer(pos)
+            assert np.array_equal(tr.cpu().numpy(), t_ref)
+            assert np.array_equal(sl.cpu().numpy(), s_ref)
+
+
+@pytest.mark.parametrize("ncols,trainers", [(64, 1), (64, 3), (17, 2), (63, 1), (200, 2), (4, 1)])
+def test_fast_f32_scatter_matches_golden(tmp_path_factory, ncols, trainers):
+    files = _float_files(tmp_path_factory, ncols)
+    cols = [f"f{i}" for i in range(ncols - 1)] + ["labels"]
+    cpu, dev = _engines(files, _f32_layout(cols), trainers)
+    assert dev.fast_mode == 0 and not dev.generic_field_idx
+    try:
+        _compare_epochs(cpu, dev)
+    finally:
+        dev.close(); cpu.close()
+
+
+@pytest.mark.parametrize("ncols", [64, 40, 130])
+def test_fast_bf16_scatter_matches_golden(tmp_path_factory, ncols):
+    files = _float_files(tmp_path_factory, ncols, name="b")
+    cols = [f"f{i}" for i in range(ncols - 1)] + ["labels"]
+    cpu, dev = _engines(files, _f32_layout(cols, L.DT_BF16), 2)
+    assert dev.fast_mode == 1
+    try:
+        _compare_epochs(cpu, dev, epochs=(0, 1))
+    finally:
+        dev.close(); cpu.close()
+
+
+@pytest.mark.parametrize("ncols", [64, 128, 100, 300])
+def test_fast_fp8_block_scaled_matches_golden(tmp_path_factory, ncols):
+    files = _float_files(tmp_path_factory, ncols, name="q")
+    cols = [f"f{i}" for i in range(ncols - 1)] + ["labels"]
+    cpu, dev = _engines(files, _f32_layout(cols, L.DT_FP8, fp8=True), 2)
+    assert dev.fast_mode == 2
+    try:
+        _compare_epochs(cpu, dev, epochs=(0, 1))
+    finally:
+        dev.close(); cpu.close()
+
+
+def test_split_fast_features_generic_label(tmp_path_factory):
+    files = _float_files(tmp_path_factory, 65, name="s")
+    feats = [f"f{i}" for i in range(64)]
+
+    def fn(schema):
+        return L.build_layout([(c, L.DT_F32, L.DT_BF16, 1) for c in feats]
+                              + [("labels", L.DT_F32, L.DT_F32, 1), ("key", L.DT_I64, L.DT_I64, 1)])
+    cpu, dev = _engines(files, fn, 2)
+    assert dev.fast_mode == 1 and len(dev.generic_field_idx) == 2
+    try:
+        _compare_epochs(cpu, dev, epochs=(0, 1))
+    finally:
+        dev.close(); cpu.close()
+
+
+def test_generic_data_spec_matches_golden(small_dataset):
+    files, n = small_dataset
+    cpu, dev = _engines(files, L.dataframe_layout, 3)
+    assert dev.fast_mode == -1
+    try:
+        _compare_epochs(cpu, dev)
+    finally:
+        dev.close(); cpu.close()
+
+
+def test_generic_casts_match_golden(small_dataset):
+    files, n = small_dataset
+
+    def fn(schema):
+        return L.build_layout([
+            ("embeddings_name0", L.DT_I64, L.DT_F32, 1), ("embeddings_name12", L.DT_I64, L.DT_I32, 1),
+            ("labels", L.DT_F64, L.DT_F32, 1), ("labels", L.DT_F64, L.DT_BF16, 1),
+            ("one_hot0", L.DT_I64, L.DT_U8, 1), ("labels", L.DT_F64, L.DT_F16, 1),
+            ("embeddings_name3", L.DT_I64, L.DT_F64, 1), ("key", L.DT_I64, L.DT_I64, 1),
+            ("one_hot1", L.DT_I64, L.DT_BOOL, 1), ("embeddings_name1", L.DT_I64, L.DT_I16, 1)])
+    cpu, dev = _engines(files, fn, 2)
+    try:
+        _compare_epochs(cpu, dev, epochs=(0,))
+    finally:
+        dev.close(); cpu.close()
+
+
+def test_forced_generic_equals_fast(tmp_path_factory):
+    files = _float_files(tmp_path_factory, 64, name="g")
+    cols = [f"f{i}" for i in range(63)] + ["labels"]
+    cpu, dev = _engines(files, _f32_layout(cols), 2, force_generic=True)
+    assert dev.fast_mode == -1
+    try:
+        _compare_epochs(cpu, dev, epochs=(0,))
+    finally:
+        dev.close(); cpu.close()
+
+
+def test_streaming_host_resident_matches_golden(tmp_path_factory):
+    files = _float_files(tmp_path_factory, 32, name="h")
+    cols = [f"f{i}" for i in range(31)] + ["labels"]
+    cpu, dev = _engines(files, _f32_layout(cols), 2, resident="host", stream_chunk_rows=3000)
+    assert dev.h2d_bytes_per_epoch() == 20_011 * 32 * 4
+    try:
+        _compare_epochs(cpu, dev, epochs=(0, 1, 2, 3))
+    finally:
+        dev.close(); cpu.close()
+
+
+def test_nccl_baseline_single_gpu_matches_golden(tmp_path_factory):
+    files = _float_files(tmp_path_factory, 64, name="n")
+    cols = [f"f{i}" for i in range(63)] + ["labels"]
+    cpu, dev = _engines(files, _f32_layout(cols), 2, exchange="nccl")
+    try:
+        _compare_epochs(cpu, dev, epochs=(0, 1))
+    finally:
+        dev.close(); cpu.close()
+
+
+def test_stream_wait_mode(tmp_path_factory):
+    files = _float_files(tmp_path_factory, 64, name="w")
+    cols = [f"f{i}" for i in range(63)] + ["labels"]
+    cpu, dev = _engines(files, _f32_layout(cols), 1, wait_mode="stream")
+    try:
+        _compare_epochs(cpu, dev, epochs=(0, 1, 2))
+        dev.check_error()
+    finally:
+        dev.close(); cpu.close()
