@@ -161,12 +161,17 @@ class FlagPoller {
     const auto t0 = std::chrono::steady_clock::now();
     int sleep_us = 5;
     for (;;) {
-      check(cudaMemcpyAsync(scratch_, dev_flags, count * sizeof(uint32_t), cudaMemcpyDeviceToHost,
-                            stream_), "cudaMemcpyAsync(flags)");
-      check(cudaStreamSynchronize(stream_), "cudaStreamSynchronize(flags)");
       int lagging = -1;
-      for (uint32_t i = 0; i < count; ++i)
-        if (static_cast<int32_t>(scratch_[i] - value) < 0) { lagging = static_cast<int>(i); break; }
+      {
+        // several consumer threads may poll through one engine: the scratch
+        // buffer and the stream are shared
+        std::lock_guard<std::mutex> g(mu_);
+        check(cudaMemcpyAsync(scratch_, dev_flags, count * sizeof(uint32_t),
+                              cudaMemcpyDeviceToHost, stream_), "cudaMemcpyAsync(flags)");
+        check(cudaStreamSynchronize(stream_), "cudaStreamSynchronize(flags)");
+        for (uint32_t i = 0; i < count; ++i)
+          if (static_cast<int32_t>(scratch_[i] - value) < 0) { lagging = static_cast<int>(i); break; }
+      }
       if (lagging < 0) return -1;
       const double waited =
           std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -176,6 +181,7 @@ class FlagPoller {
     }
   }
   std::vector<uint32_t> read(const uint32_t* dev_flags, uint32_t count) {
+    std::lock_guard<std::mutex> g(mu_);
     check(cudaMemcpyAsync(scratch_, dev_flags, count * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                           stream_), "cudaMemcpyAsync(flags)");
     check(cudaStreamSynchronize(stream_), "cudaStreamSynchronize(flags)");
@@ -185,6 +191,7 @@ class FlagPoller {
  private:
   uint32_t* scratch_ = nullptr;
   cudaStream_t stream_ = nullptr;
+  std::mutex mu_;
 };
 
 }  // namespace
@@ -365,6 +372,10 @@ PYBIND11_MODULE(_C, m) {
                             uintptr_t out, uintptr_t stream) {
     rsdl::launch_batch_sum_f32(as_ptr<const uint8_t>(packed), rows, pitch, off,
                                as_ptr<double>(out), as_stream(stream));
+  });
+  m.def("batch_sum_all_f32", [](uintptr_t packed, uint64_t nbytes, uintptr_t out, uintptr_t stream) {
+    rsdl::launch_batch_sum_all_f32(as_ptr<const uint8_t>(packed), nbytes, as_ptr<double>(out),
+                                   as_stream(stream));
   });
   m.def("signal_flags", [](const std::vector<uintptr_t>& ptrs, uint32_t value, uintptr_t stream) {
     if (ptrs.size() > RSDL_MAX_TRAINERS) throw std::runtime_error("too many flag targets");

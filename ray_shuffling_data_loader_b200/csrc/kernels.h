@@ -64,6 +64,8 @@ void launch_key_checksum(const uint8_t* packed, unsigned long long rows, uint32_
                          uint32_t key_off, unsigned long long* out, cudaStream_t stream);
 void launch_batch_sum_f32(const uint8_t* packed, unsigned long long rows, uint32_t pitch,
                           uint32_t off, double* out, cudaStream_t stream);
+void launch_batch_sum_all_f32(const uint8_t* packed, unsigned long long nbytes, double* out,
+                              cudaStream_t stream);
 void launch_signal_flags(const FlagTargets& t, uint32_t value, cudaStream_t stream);
 void launch_wait_flags(const uint32_t* flags, uint32_t count, uint32_t value,
                        unsigned long long timeout_ns, uint32_t* error, cudaStream_t stream);

@@ -502,6 +502,27 @@ __global__ void batch_sum_f32_kernel(const uint8_t* packed, unsigned long long r
   if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
 }
 
+// Full-batch sink: fp64 sum of every fp32 word of a packed batch (reads the
+// whole batch once, 16 B per lane - the "trainer touched every byte" proof).
+__global__ void batch_sum_all_f32_kernel(const float4* data, unsigned long long nvec, double* out) {
+  double s = 0.0;
+  for (unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+       i < nvec; i += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
+    float4 v = __ldg(data + i);
+    s += static_cast<double>(v.x) + static_cast<double>(v.y) + static_cast<double>(v.z) +
+         static_cast<double>(v.w);
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __shared__ double part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) t += part[w];
+    atomicAdd(out, t);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // K11 device ring signalling: epoch-tagged flags in (peer) HBM
 // ---------------------------------------------------------------------------
@@ -624,6 +645,15 @@ void launch_batch_sum_f32(const uint8_t* packed, unsigned long long rows, uint32
   int grid = static_cast<int>(std::min<unsigned long long>((rows + 255) / 256, 148 * 4));
   batch_sum_f32_kernel<<<grid, 256, 0, stream>>>(packed, rows, pitch, off, out);
   check_launch("batch_sum_f32");
+}
+
+void launch_batch_sum_all_f32(const uint8_t* packed, unsigned long long nbytes, double* out,
+                              cudaStream_t stream) {
+  const unsigned long long nvec = nbytes / 16;
+  if (nvec == 0) return;
+  int grid = static_cast<int>(std::min<unsigned long long>((nvec + 255) / 256, 148 * 8));
+  batch_sum_all_f32_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(packed), nvec, out);
+  check_launch("batch_sum_all_f32");
 }
 
 void launch_signal_flags(const FlagTargets& t, uint32_t value, cudaStream_t stream) {

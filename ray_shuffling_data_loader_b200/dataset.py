@@ -156,10 +156,10 @@ class ShufflingDataset:
                 num_epochs, num_trainers, max_concurrent_epochs,
                 name=name, connect=True)
             self._seed = seed
-            device = "cpu"
-        if output is None:
+            device = None      # decided by the first chunk that arrives
+        if output is None and device is not None:
             output = "pandas" if device == "cpu" else "device"
-        if output not in ("pandas", "device", "packed"):
+        if output not in (None, "pandas", "device", "packed"):
             raise ValueError(f"unknown output {output!r}")
         self._output = output
 
@@ -216,6 +216,9 @@ class ShufflingDataset:
         self._skip_batches = int(state.get("batches_consumed", 0))
 
     def _convert(self, packed, layout):
+        if self._output is None:
+            import numpy as np
+            self._output = "pandas" if isinstance(packed, np.ndarray) else "device"
         if self._output == "packed":
             return packed
         if self._output == "device":
@@ -324,7 +327,9 @@ class ShufflingDataset:
             self._driver.join()
             self._raise_driver_error()
             self._driver = None
-        self._engine.close()
+        # Batches the caller still holds stay valid: device memory is released
+        # by close() / garbage collection, not here.
+        self._engine.quiesce()
         try:
             self._batch_queue.shutdown()
         except Exception:
@@ -334,15 +339,24 @@ class ShufflingDataset:
         """Tear down early (the last epoch's iterator does this itself)."""
         if self._engine is None:
             return
+        if hasattr(self._engine, "cancel") and self._driver is not None:
+            self._engine.cancel()
         try:
             self._batch_queue.shutdown()
         except Exception:
             pass
         if self._driver is not None:
-            self._driver.join(timeout=30)
+            self._driver.join(timeout=60)
             self._driver = None
         if self._engine is not None:
             self._engine.close()
+
+    def __del__(self):
+        try:
+            if self._engine is not None and self._driver is None:
+                self._engine.close()
+        except Exception:
+            pass
 
 
 class _Rebatcher:

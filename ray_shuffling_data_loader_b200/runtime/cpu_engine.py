@@ -159,6 +159,9 @@ class CpuShuffleEngine:
         base = self._packed.nbytes if self._packed is not None else 0
         return base + max(0, self._bytes_in_flight)
 
+    def quiesce(self):
+        pass
+
     def close(self):
         if not self._closed:
             self._closed = True

@@ -418,8 +418,8 @@ class DeviceShuffleEngine:
         if epoch >= self.window:
             # Back-pressure: every trainer must have released this slot's
             # previous epoch before any source may overwrite it.
-            lag = self.poller.wait(self._consumed_ptr(self.rank, 0), plan.num_trainers,
-                                   epoch - self.window + 1, self.flag_timeout_s)
+            lag = self._poll(self._consumed_ptr(self.rank, 0), plan.num_trainers,
+                             epoch - self.window + 1, self.flag_timeout_s)
             if lag >= 0:
                 raise TimeoutError(
                     f"trainer {lag} did not release epoch {epoch - self.window} within "
@@ -483,6 +483,22 @@ class DeviceShuffleEngine:
         return int(sum(self.n_local * L.itemsize(f.src_code) * f.width
                        for f in self.src_fields))
 
+    def cancel(self):
+        """Make every pending flag wait fail fast (early teardown)."""
+        self._cancelled = True
+
+    def _poll(self, ptr: int, count: int, value: int, timeout_s: float) -> int:
+        """Host-side flag wait in short native slices so teardown can interrupt
+        it; returns -1 when all flags reached ``value`` else the lagging index."""
+        deadline = timeit.default_timer() + timeout_s
+        while True:
+            if getattr(self, "_cancelled", False) or self._closed:
+                raise RuntimeError("shuffle engine is shutting down")
+            remaining = deadline - timeit.default_timer()
+            lag = self.poller.wait(ptr, count, value, max(0.0, min(0.05, remaining)))
+            if lag < 0 or remaining <= 0:
+                return lag
+
     def _make_wait(self, epoch: int, slot: int, t_start: float):
         state = {"done": False}
 
@@ -499,8 +515,8 @@ class DeviceShuffleEngine:
                 self.launches += 1
             else:
                 limit = self.flag_timeout_s if timeout is None else timeout
-                lag = self.poller.wait(self._produced_ptr(self.rank, slot, 0), self.world,
-                                       epoch + 1, limit)
+                lag = self._poll(self._produced_ptr(self.rank, slot, 0), self.world,
+                                 epoch + 1, limit)
                 if lag >= 0:
                     raise TimeoutError(
                         f"source rank {lag} did not deliver epoch {epoch} within {limit}s")
@@ -582,30 +598,53 @@ class DeviceShuffleEngine:
         self.launches += 1
         return out
 
+    def batch_sum_all(self, packed, out):
+        """fp64 sum of every fp32 word of a packed fp32 batch, accumulated into
+        ``out`` (1-element float64 CUDA tensor) on the current stream."""
+        self.C.batch_sum_all_f32(packed.data_ptr(), packed.shape[0] * packed.shape[1],
+                                 out.data_ptr(),
+                                 self.torch.cuda.current_stream().cuda_stream)
+        self.launches += 1
+        return out
+
     def bytes_in_use(self) -> int:
         if self._closed:
             return 0
         return int(self.arena_bytes + self.src_arena_bytes)
 
+    def quiesce(self):
+        """End of the last epoch: drain our streams, wait (collectively) until no
+        peer can still push into us, and drop the peer mappings. Our own arena
+        stays allocated so batches the user still holds remain valid until
+        ``close()``."""
+        if self._closed or getattr(self, "_quiesced", False):
+            return
+        self._quiesced = True
+        C = self.C
+        C.set_device(self.device_index)
+        C.stream_synchronize(self.shuffle_stream)
+        C.stream_synchronize(self.copy_stream)
+        self.torch.cuda.synchronize(self.device_index)
+        if self.world > 1:
+            bootstrap.barrier(self.pg)
+        for base in self._opened:
+            try:
+                C.ipc_close_handle(base)
+            except Exception:
+                pass
+        self._opened = []
+
     def close(self):
+        """Free every device / pinned allocation (not collective once
+        ``quiesce`` ran)."""
         if self._closed:
             return
-        self._closed = True
-        stats_mod.unregister_bytes_used_source(self._bytes_fn)
-        C = self.C
         try:
-            C.stream_synchronize(self.shuffle_stream)
-            C.stream_synchronize(self.copy_stream)
-            self.torch.cuda.synchronize(self.device_index)
-            if self.world > 1:
-                # nobody may unmap/free while a peer can still push into us
-                bootstrap.barrier(self.pg)
+            self.quiesce()
         finally:
-            for base in self._opened:
-                try:
-                    C.ipc_close_handle(base)
-                except Exception:
-                    pass
+            self._closed = True
+            stats_mod.unregister_bytes_used_source(self._bytes_fn)
+            C = self.C
             for ev in self._events.values():
                 C.event_destroy(ev[0])
                 C.event_destroy(ev[1])
@@ -622,6 +661,13 @@ class DeviceShuffleEngine:
             C.device_free(self.arena)
             C.stream_destroy(self.shuffle_stream)
             C.stream_destroy(self.copy_stream)
+
+    def __del__(self):
+        try:
+            if not self._closed and getattr(self, "_quiesced", False):
+                self.close()
+        except Exception:
+            pass
 
 
 def _pad(b: bytes, a: int = 256) -> bytes:

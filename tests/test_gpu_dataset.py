@@ -33,9 +33,11 @@ def test_device_batches_exactly_once(small_dataset):
         assert np.array_equal(np.sort(keys), np.arange(n))
         assert prev is None or not np.array_equal(keys, prev)
         prev = keys
-    # to_pandas round trip keeps rows intact
+    # batches held after the final epoch stay valid until the dataset is closed
     df = b.to_pandas()
     assert list(df.columns) == ["key"] + list(DATA_SPEC.keys())
+    assert np.array_equal(df["key"].to_numpy(), keys[-len(df):])
+    ds.close()
 
 
 def test_gpu_equals_cpu_batches(small_dataset):
@@ -108,17 +110,22 @@ def test_window_backpressure_many_epochs(float_dataset):
     out = {}
 
     def run(d, r):
-        sums = []
-        for epoch in range(7):
-            d.set_epoch(epoch)
-            ks = [b["key"].clone() for b in d]
-            sums.append(torch.cat(ks).cpu().numpy())
-        out[r] = sums
-    # rank 1 shares the engine's device: make its batches torch views too
+        try:
+            sums = []
+            for epoch in range(7):
+                d.set_epoch(epoch)
+                ks = [b["key"].clone() for b in d]
+                sums.append(torch.cat(ks).cpu().numpy())
+            out[r] = sums
+        except BaseException as e:   # never leave the other trainer blocked
+            out[r] = e
+            ds.close()
     t = threading.Thread(target=run, args=(ds1, 1))
     t.start()
     run(ds, 0)
     t.join(timeout=120)
+    for r in (0, 1):
+        assert not isinstance(out.get(r), BaseException), out[r]
     for epoch in range(7):
         keys = np.concatenate([out[0][epoch], out[1][epoch]])
         assert np.array_equal(np.sort(keys), np.arange(n)), epoch

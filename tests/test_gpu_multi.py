@@ -1,0 +1,81 @@
+"""Multi-GPU tests (>= 2 B200): the P2P scatter over NVLink and the NCCL
+baseline both reproduce the numpy golden on every rank. One process per GPU,
+``torch.multiprocessing.spawn`` standing in for the cluster."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu,
+              pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2,
+                                 reason="needs >= 2 CUDA devices")]
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, files, ncols, dst_code, fp8, exchange, resident, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch
+    import torch.distributed as dist
+    from ray_shuffling_data_loader_b200.ops import layout as L
+    from ray_shuffling_data_loader_b200.runtime.cpu_engine import CpuShuffleEngine
+    from ray_shuffling_data_loader_b200.runtime.device_engine import DeviceShuffleEngine
+    torch.cuda.set_device(rank)
+    dist.init_process_group("cuda:nccl,cpu:gloo", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    cols = [f"f{i}" for i in range(ncols - 1)] + ["labels"]
+
+    def fn(schema):
+        return L.build_layout([(c, schema[c][0], dst_code, 1) for c in cols],
+                              fp8_block_scale=fp8)
+    plan_args = dict(num_trainers=world, num_reducers=world, batch_size=1000, drop_last=False)
+    gold = CpuShuffleEngine(files, plan_args, fn, 42)          # all trainers, one process
+    opts = dict(exchange=exchange, resident=resident)
+    if resident == "host":
+        opts["stream_chunk_rows"] = 4096
+    dev = DeviceShuffleEngine(files, plan_args, fn, 42, rank=rank, world=world, **opts)
+    ok = True
+    for epoch in range(4):                                      # > window: slots get reused
+        gb = gold.start_epoch(epoch)
+        db = dev.start_epoch(epoch)
+        gb[rank].wait(120)
+        db[rank].wait(120)
+        got = db[rank].data.cpu().numpy()
+        ok = ok and np.array_equal(got, gb[rank].data)
+        db[rank].release()
+    torch.cuda.synchronize()
+    dev.close()
+    gold.close()
+    with open(os.path.join(out_dir, f"ok_{rank}"), "w") as f:
+        f.write("1" if ok else "0")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _files(tmp_path_factory, ncols, nrows=60_013):
+    from ray_shuffling_data_loader_b200.data_generation import generate_data, float_spec
+    d = tmp_path_factory.mktemp(f"multi{ncols}")
+    files, _ = generate_data(nrows, 4, 2, 0.0, str(d), data_spec=float_spec(ncols, np.float32),
+                             seed=ncols)
+    return files
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("exchange,resident,dst,fp8", [
+    ("p2p", "hbm", 7, False), ("p2p", "host", 7, False), ("p2p", "hbm", 6, False),
+    ("p2p", "hbm", 9, True), ("nccl", "hbm", 7, False)])
+def test_multi_gpu_matches_golden(tmp_path_factory, tmp_path, exchange, resident, dst, fp8):
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 8)
+    files = _files(tmp_path_factory, 64)
+    mp.spawn(_worker, args=(world, _free_port(), files, 64, dst, fp8, exchange, resident,
+                            str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert open(tmp_path / f"ok_{r}").read() == "1", f"rank {r} mismatch"
