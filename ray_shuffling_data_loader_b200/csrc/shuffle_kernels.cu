@@ -87,6 +87,16 @@ __device__ __forceinline__ float4 lds128(const float* p) {
   return v;
 }
 
+__device__ __forceinline__ unsigned long long lds64(const void* p) {
+  unsigned long long v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(smem_u32(p)));
+  return v;
+}
+
+__device__ __forceinline__ void sts64(void* p, unsigned long long v) {
+  asm volatile("st.shared.u64 [%0], %1;" ::"r"(smem_u32(p)), "l"(v) : "memory");
+}
+
 // 16-byte store to a (possibly peer-mapped) global address.
 __device__ __forceinline__ void stg128(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c),
@@ -132,7 +142,8 @@ dest_pointer(unsigned long long gi, const PermKeyDev& key, const PlanDev& plan,
 constexpr int kTileRows = 128;
 constexpr int kPitchWords = kTileRows + 4;   // shared-memory words per column
 constexpr int kConsumerWarps = 8;
-constexpr int kThreads = 32 * (1 + kConsumerWarps);
+constexpr int kIndexWarps = kTileRows / 32;   // one destination pointer per thread per tile
+constexpr int kThreads = 32 * (1 + kIndexWarps + kConsumerWarps);
 
 template <int MODE> struct ModeTraits;
 template <> struct ModeTraits<0> { static constexpr int FPL = 4;  static constexpr int PANEL = 64;  static constexpr int STAGES = 4; };
@@ -145,8 +156,9 @@ struct alignas(128) FastSmem {
   static constexpr int STAGES = ModeTraits<MODE>::STAGES;
   float tile[STAGES][PANEL * kPitchWords];
   unsigned long long dptr[STAGES][kTileRows];
-  uint64_t full[STAGES];
-  uint64_t empty[STAGES];
+  uint64_t full[STAGES];       // TMA bytes landed
+  uint64_t idx_full[STAGES];   // destination pointers written
+  uint64_t empty[STAGES];      // consumers done with the stage
 };
 
 template <int MODE>
@@ -166,6 +178,7 @@ __global__ void __launch_bounds__(kThreads, 1) scatter_tma_kernel(const FastPara
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&sm.full[s], 1);
+      mbar_init(&sm.idx_full[s], kIndexWarps);
       mbar_init(&sm.empty[s], kConsumerWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -176,30 +189,14 @@ __global__ void __launch_bounds__(kThreads, 1) scatter_tma_kernel(const FastPara
   const unsigned long long num_items = num_tiles * p.num_panels;
 
   if (warp == 0) {
-    // ===== producer: destination pointers + TMA bulk loads =====
+    // ===== producer: TMA bulk loads of the columnar tile =====
     int stage = 0;
     uint32_t phase = 0;
-    unsigned long long prev_tile = ~0ull;
-    int prev_stage = 0;
     for (unsigned long long item = blockIdx.x; item < num_items; item += gridDim.x) {
       const unsigned long long tile = item / p.num_panels;
       const uint32_t panel = static_cast<uint32_t>(item - tile * p.num_panels);
       mbar_wait(&sm.empty[stage], phase ^ 1);
       const unsigned long long row0 = tile * kTileRows;
-      if (tile == prev_tile) {
-        // Same rows, next column panel: reuse the shared permutation index.
-        for (int r = lane; r < kTileRows; r += 32) sm.dptr[stage][r] = sm.dptr[prev_stage][r];
-      } else {
-        for (int r = lane; r < kTileRows; r += 32) {
-          const unsigned long long lr = row0 + r;
-          sm.dptr[stage][r] = (lr < p.n_local)
-              ? dest_pointer(p.global_offset + lr, p.key, p.plan, p.dst, p.row_pitch)
-              : 0ull;
-        }
-      }
-      prev_tile = tile;
-      prev_stage = stage;
-      __syncwarp();
       const uint32_t col0 = panel * PANEL;
       const uint32_t ncols = min(static_cast<uint32_t>(PANEL), p.num_cols - col0);
       if (lane == 0) mbar_arrive_expect_tx(&sm.full[stage], ncols * kTileRows * 4u);
@@ -210,9 +207,33 @@ __global__ void __launch_bounds__(kThreads, 1) scatter_tma_kernel(const FastPara
       }
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
+  } else if (warp <= kIndexWarps) {
+    // ===== index warps: the tile's shared permutation index =====
+    // One Feistel evaluation per thread per tile, running STAGES tiles ahead of
+    // the consumers; column panels of the same rows reuse the previous result.
+    const int r = threadIdx.x - 32;            // row inside the tile
+    int stage = 0;
+    uint32_t phase = 0;
+    unsigned long long prev_tile = ~0ull;
+    unsigned long long prev = 0;
+    for (unsigned long long item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const unsigned long long tile = item / p.num_panels;
+      mbar_wait(&sm.empty[stage], phase ^ 1);
+      if (tile != prev_tile) {
+        const unsigned long long lr = tile * kTileRows + r;
+        prev = (lr < p.n_local)
+            ? dest_pointer(p.global_offset + lr, p.key, p.plan, p.dst, p.row_pitch)
+            : 0ull;
+        prev_tile = tile;
+      }
+      sts64(&sm.dptr[stage][r], prev);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.idx_full[stage]);
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
   } else {
     // ===== consumers: transpose + cast + scatter =====
-    const int cwarp = warp - 1;
+    const int cwarp = warp - 1 - kIndexWarps;
     const int rho = lane & 3;
     const int q = lane >> 2;
     int stage = 0;
@@ -222,13 +243,14 @@ __global__ void __launch_bounds__(kThreads, 1) scatter_tma_kernel(const FastPara
       const uint32_t panel = static_cast<uint32_t>(item - tile * p.num_panels);
       const uint32_t col0 = panel * PANEL;
       const uint32_t ncols = min(static_cast<uint32_t>(PANEL), p.num_cols - col0);
+      mbar_wait(&sm.idx_full[stage], phase);
       mbar_wait(&sm.full[stage], phase);
       const float* A = sm.tile[stage];
       for (int step = cwarp; step < kTileRows / 16; step += kConsumerWarps) {
         const int rg = step * 4 + rho;            // 4-row group inside the tile
         unsigned long long d[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) d[j] = sm.dptr[stage][rg * 4 + j];
+        for (int j = 0; j < 4; ++j) d[j] = lds64(&sm.dptr[stage][rg * 4 + j]);
 #pragma unroll
         for (int pass = 0; pass < PASSES; ++pass) {
           const int cb = q + 8 * pass;            // column block inside the panel

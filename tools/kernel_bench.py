@@ -1,0 +1,109 @@
+#!/usr/bin/env python
+"""Micro-benchmark of the scatter kernels on synthetic device-resident columns
+(no Parquet, no queue): CUDA-event timing, GB/s and fraction of the measured HBM
+copy peak. Used under gpurun and as the ncu target.
+
+    python tools/kernel_bench.py --rows 12500000 --cols 64 --mode 0 --iters 10
+"""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import numpy as np
+import torch
+
+from ray_shuffling_data_loader_b200 import _C
+from ray_shuffling_data_loader_b200.ops import perm
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rows", type=int, default=12_500_000)
+    ap.add_argument("--cols", type=int, default=64)
+    ap.add_argument("--mode", type=int, default=0, help="0 f32, 1 bf16, 2 fp8 block-scaled, 3 generic f32")
+    ap.add_argument("--trainers", type=int, default=1)
+    ap.add_argument("--grid", type=int, default=0)
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--verify", action="store_true")
+    a = ap.parse_args()
+    torch.cuda.set_device(0)
+    _C.set_device(0)
+    sm = _C.sm_count(0)
+    n, F = a.rows, a.cols
+    rows_pad = (n + 255) // 256 * 256
+    src = torch.rand((F, rows_pad), dtype=torch.float32, device="cuda")
+    dsz = {0: 4, 1: 2, 2: 1, 3: 4}[a.mode]
+    payload = F * dsz
+    scale_off = (payload + 15) // 16 * 16
+    pitch = ((scale_off + (F + 31) // 32 if a.mode == 2 else payload) + 15) // 16 * 16
+    T = a.trainers
+    per = -(-n // T)
+    dst = torch.zeros((T, per, pitch), dtype=torch.uint8, device="cuda")
+    ptrs = torch.tensor([src[c].data_ptr() for c in range(F)], dtype=torch.int64, device="cuda")
+    dst_ptrs = [dst[t].data_ptr() for t in range(T)]
+    stream = torch.cuda.current_stream().cuda_stream
+    fields = None
+    if a.mode == 3:
+        dt = np.dtype([("src", "<u8"), ("src_code", "<u4"), ("dst_code", "<u4"),
+                       ("dst_off", "<u4"), ("width", "<u4")])
+        arr = np.zeros(F, dtype=dt)
+        for c in range(F):
+            arr[c] = (src[c].data_ptr(), 7, 7, 4 * c, 1)
+        fields = torch.from_numpy(arr.view(np.uint8).copy()).cuda()
+
+    def launch(epoch):
+        key = list(perm.make_key(n, 1234, epoch).as_words())
+        if a.mode == 3:
+            _C.scatter_generic(key=key, num_rows=n, num_trainers=T, fields=fields.data_ptr(),
+                               num_fields=F, n_local=n, global_offset=0, row_pitch=pitch,
+                               write_lo=0, write_hi=pitch, dst=dst_ptrs,
+                               grid=a.grid or sm * 2, stream=stream)
+        else:
+            tiles = -(-n // _C.TILE_ROWS) * -(-F // _C.fast_panel_cols(a.mode))
+            _C.scatter_fast(key=key, num_rows=n, num_trainers=T, cols=ptrs.data_ptr(),
+                            num_cols=F, n_local=n, global_offset=0, row_pitch=pitch,
+                            scale_offset=scale_off, dst=dst_ptrs, mode=a.mode,
+                            grid=min(a.grid or sm, tiles), stream=stream)
+    for i in range(a.warmup):
+        launch(i)
+    torch.cuda.synchronize()
+    times = []
+    for i in range(a.iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        launch(100 + i)
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    if a.verify and a.mode in (0, 3):
+        launch(7)
+        torch.cuda.synchronize()
+        pos = perm.permute(np.arange(min(n, 100000), dtype=np.uint64), perm.make_key(n, 1234, 7))
+        q, rem = divmod(n, T)
+        assert rem == 0 or T == 1
+        got = dst.view(-1, pitch)[torch.from_numpy(pos.astype(np.int64)).cuda()] \
+            .view(torch.float32)[:, :F]
+        want = src[:, :len(pos)].t()
+        assert torch.equal(got, want), "scatter mismatch"
+    bytes_moved = n * (F * 4 + pitch)
+    best, med = min(times), sorted(times)[len(times) // 2]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(
+            os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    out = {"rows": n, "cols": F, "mode": a.mode, "trainers": T, "row_pitch": pitch,
+           "ms_best": best, "ms_median": med, "gbps_best": bytes_moved / best / 1e6,
+           "gbps_median": bytes_moved / med / 1e6, "bytes": bytes_moved, "grid": a.grid or sm}
+    if peaks.get("hbm_gbs"):
+        out["frac_of_measured_hbm_peak"] = out["gbps_best"] / peaks["hbm_gbs"]
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
