@@ -47,8 +47,11 @@ METRIC = "rows_per_sec"
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=100)
-    p.add_argument("--warmup", type=int, default=10)
+    # Defaults: warm up for 2 whole epochs (50 batches each) so the epoch ring is
+    # in steady state - nothing consumed in the timed region was shuffled before
+    # it started - then time 4 whole epochs.
+    p.add_argument("--steps", type=int, default=200)
+    p.add_argument("--warmup", type=int, default=100)
     p.add_argument("--impl", choices=["ours", "reference"], default="ours")
     p.add_argument("--rows-per-gpu", type=int, default=ROWS_PER_GPU)
     p.add_argument("--cols", type=int, default=NUM_COLS)

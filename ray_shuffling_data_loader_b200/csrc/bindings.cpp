@@ -64,6 +64,41 @@ PlanDev make_plan(uint64_t num_rows, uint32_t num_trainers) {
   return p;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link).
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || p == nullptr)
+      throw std::runtime_error("cuTensorMapEncodeTiled is not available from this driver");
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// 2-D view [num_cols][rows_alloc] of 4-byte source columns with a uniform
+// stride; boxes are [panel cols][32 rows] = 128-byte rows, 128-byte swizzle.
+void make_source_tmap(CUtensorMap* map, uintptr_t base, uint64_t rows_alloc, uint32_t num_cols,
+                      uint64_t col_stride_bytes, uint32_t panel_cols) {
+  cuuint64_t dims[2] = {rows_alloc, num_cols};
+  cuuint64_t strides[1] = {col_stride_bytes};
+  cuuint32_t box[2] = {32, panel_cols};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode_tiled_fn()(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2,
+                                 reinterpret_cast<void*>(base), dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    throw std::runtime_error("cuTensorMapEncodeTiled failed with code " + std::to_string(r));
+}
+
 template <typename P>
 void fill_dst(P& p, const std::vector<uintptr_t>& dst) {
   if (dst.size() > RSDL_MAX_TRAINERS) throw std::runtime_error("too many trainers");
@@ -307,8 +342,16 @@ PYBIND11_MODULE(_C, m) {
         [](const std::vector<uint64_t>& key, uint64_t num_rows, uint32_t num_trainers,
            uintptr_t cols, uint32_t num_cols, uint64_t n_local, uint64_t global_offset,
            uint32_t row_pitch, uint32_t scale_offset, const std::vector<uintptr_t>& dst, int mode,
-           int grid, uintptr_t stream) {
+           int grid, uintptr_t stream, uintptr_t col_base, uint64_t col_stride,
+           uint64_t rows_alloc) {
           FastParams p;
+          std::memset(&p.tmap, 0, sizeof(p.tmap));
+          p.use_tmap = 0;
+          if (col_base != 0 && col_stride % 16 == 0 && rows_alloc % 32 == 0) {
+            make_source_tmap(&p.tmap, col_base, rows_alloc, num_cols, col_stride,
+                             static_cast<uint32_t>(rsdl::fast_panel_cols(mode)));
+            p.use_tmap = 1;
+          }
           p.key = make_key(key);
           p.plan = make_plan(num_rows, num_trainers);
           p.cols = as_ptr<const uint8_t* const>(cols);
@@ -325,7 +368,9 @@ PYBIND11_MODULE(_C, m) {
         py::arg("key"), py::arg("num_rows"), py::arg("num_trainers"), py::arg("cols"),
         py::arg("num_cols"), py::arg("n_local"), py::arg("global_offset"), py::arg("row_pitch"),
         py::arg("scale_offset"), py::arg("dst"), py::arg("mode"), py::arg("grid"),
-        py::arg("stream"));
+        py::arg("stream"), py::arg("col_base") = 0, py::arg("col_stride") = 0,
+        py::arg("rows_alloc") = 0);
+  m.def("fast_ctas_per_sm", &rsdl::fast_ctas_per_sm);
   m.def("scatter_generic",
         [](const std::vector<uint64_t>& key, uint64_t num_rows, uint32_t num_trainers,
            uintptr_t fields, uint32_t num_fields, uint64_t n_local, uint64_t global_offset,

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "common.cuh"
@@ -11,6 +12,8 @@ namespace rsdl {
 
 // Fast path: every source column is a 4-byte scalar (see shuffle_kernels.cu).
 struct FastParams {
+  alignas(64) CUtensorMap tmap;      // [num_cols][rows] view of the source columns
+  uint32_t use_tmap;                 // 0: 1-D bulk copies from `cols` pointers
   PermKeyDev key;
   PlanDev plan;
   const uint8_t* const* cols;        // device array [num_cols] of column bases
@@ -51,6 +54,7 @@ struct FlagTargets {
 };
 
 int fast_panel_cols(int mode);
+int fast_ctas_per_sm(int mode);
 int fast_tile_rows();
 
 void launch_scatter_fast(const FastParams& p, int mode, int grid, cudaStream_t stream);

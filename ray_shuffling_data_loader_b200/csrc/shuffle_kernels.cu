@@ -79,6 +79,16 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
       : "memory");
 }
 
+// cp.async.bulk.tensor 2-D tile load through a tensor map (SASS: UTMALDG).
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, int x, int y,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(smem_dst)),
+      "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar))
+      : "memory");
+}
+
 __device__ __forceinline__ float4 lds128(const float* p) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
@@ -146,15 +156,24 @@ constexpr int kIndexWarps = kTileRows / 32;   // one destination pointer per thr
 constexpr int kThreads = 32 * (1 + kIndexWarps + kConsumerWarps);
 
 template <int MODE> struct ModeTraits;
-template <> struct ModeTraits<0> { static constexpr int FPL = 4;  static constexpr int PANEL = 64;  static constexpr int STAGES = 4; };
-template <> struct ModeTraits<1> { static constexpr int FPL = 8;  static constexpr int PANEL = 64;  static constexpr int STAGES = 4; };
-template <> struct ModeTraits<2> { static constexpr int FPL = 16; static constexpr int PANEL = 128; static constexpr int STAGES = 3; };
+template <> struct ModeTraits<0> { static constexpr int FPL = 4;  static constexpr int PANEL = 64;  static constexpr int STAGES = 3; static constexpr int MIN_CTAS = 2; };
+template <> struct ModeTraits<1> { static constexpr int FPL = 8;  static constexpr int PANEL = 64;  static constexpr int STAGES = 3; static constexpr int MIN_CTAS = 2; };
+template <> struct ModeTraits<2> { static constexpr int FPL = 16; static constexpr int PANEL = 128; static constexpr int STAGES = 3; static constexpr int MIN_CTAS = 1; };
+
+// Two shared-memory tile layouts (both conflict-free for the consumers):
+//  * tensor-map path: kTileRows/32 TMA boxes of [PANEL cols][32 rows] with the
+//    128-byte swizzle; element (c, r) of box b lives at
+//    b*PANEL*128 + c*128 + (((r%32)/4 ^ (c&7)) << 4) + (r%4)*4 bytes;
+//  * 1-D bulk path (arbitrary column pointers): column c at word c*kPitchWords.
+constexpr int kBoxRows = 32;
+constexpr int kBoxesPerTile = kTileRows / kBoxRows;
 
 template <int MODE>
-struct alignas(128) FastSmem {
+struct alignas(1024) FastSmem {
   static constexpr int PANEL = ModeTraits<MODE>::PANEL;
   static constexpr int STAGES = ModeTraits<MODE>::STAGES;
-  float tile[STAGES][PANEL * kPitchWords];
+  static constexpr int kTileWords = ((PANEL * kPitchWords + 255) / 256) * 256;
+  float tile[STAGES][kTileWords];
   unsigned long long dptr[STAGES][kTileRows];
   uint64_t full[STAGES];       // TMA bytes landed
   uint64_t idx_full[STAGES];   // destination pointers written
@@ -162,22 +181,25 @@ struct alignas(128) FastSmem {
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 1) scatter_tma_kernel(const FastParams p) {
+__global__ void __launch_bounds__(kThreads, ModeTraits<MODE>::MIN_CTAS)
+scatter_tma_kernel(const __grid_constant__ FastParams p) {
   using T = ModeTraits<MODE>;
   constexpr int FPL = T::FPL;
   constexpr int PANEL = T::PANEL;
   constexpr int STAGES = T::STAGES;
   constexpr int PASSES = PANEL / (8 * FPL);
   extern __shared__ uint8_t smem_raw[];
-  FastSmem<MODE>& sm = *reinterpret_cast<FastSmem<MODE>*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~static_cast<uintptr_t>(127));
+  // 1024-byte alignment: the 128-byte TMA swizzle is a function of address bits
+  const uint32_t raw = smem_u32(smem_raw);
+  FastSmem<MODE>& sm = *reinterpret_cast<FastSmem<MODE>*>(smem_raw + ((1024u - (raw & 1023u)) & 1023u));
+  const bool tmap = p.use_tmap != 0;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&sm.full[s], 1);
+      mbar_init(&sm.full[s], tmap ? 1 : kIndexWarps);
       mbar_init(&sm.idx_full[s], kIndexWarps);
       mbar_init(&sm.empty[s], kConsumerWarps);
     }
@@ -186,26 +208,24 @@ __global__ void __launch_bounds__(kThreads, 1) scatter_tma_kernel(const FastPara
   __syncthreads();
 
   const unsigned long long num_tiles = (p.n_local + kTileRows - 1) / kTileRows;
-  const unsigned long long num_items = num_tiles * p.num_panels;
 
   if (warp == 0) {
-    // ===== producer: TMA bulk loads of the columnar tile =====
-    int stage = 0;
-    uint32_t phase = 0;
-    for (unsigned long long item = blockIdx.x; item < num_items; item += gridDim.x) {
-      const unsigned long long tile = item / p.num_panels;
-      const uint32_t panel = static_cast<uint32_t>(item - tile * p.num_panels);
-      mbar_wait(&sm.empty[stage], phase ^ 1);
-      const unsigned long long row0 = tile * kTileRows;
-      const uint32_t col0 = panel * PANEL;
-      const uint32_t ncols = min(static_cast<uint32_t>(PANEL), p.num_cols - col0);
-      if (lane == 0) mbar_arrive_expect_tx(&sm.full[stage], ncols * kTileRows * 4u);
-      __syncwarp();
-      for (uint32_t c = lane; c < ncols; c += 32) {
-        const uint8_t* src = p.cols[col0 + c] + row0 * 4ull;
-        tma_load_1d(&sm.tile[stage][c * kPitchWords], src, kTileRows * 4u, &sm.full[stage]);
+    // ===== producer (tensor-map path): kBoxesPerTile TMA box loads per tile =====
+    if (tmap && lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap) : "memory");
+      int stage = 0;
+      uint32_t phase = 0;
+      for (unsigned long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+      for (uint32_t panel = 0; panel < p.num_panels; ++panel) {
+        mbar_wait(&sm.empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&sm.full[stage], PANEL * kTileRows * 4u);
+#pragma unroll
+        for (int b = 0; b < kBoxesPerTile; ++b)
+          tma_load_2d(&sm.tile[stage][b * PANEL * kBoxRows], &p.tmap,
+                      static_cast<int>(tile * kTileRows + b * kBoxRows),
+                      static_cast<int>(panel * PANEL), &sm.full[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
   } else if (warp <= kIndexWarps) {
     // ===== index warps: the tile's shared permutation index =====
@@ -214,22 +234,34 @@ __global__ void __launch_bounds__(kThreads, 1) scatter_tma_kernel(const FastPara
     const int r = threadIdx.x - 32;            // row inside the tile
     int stage = 0;
     uint32_t phase = 0;
-    unsigned long long prev_tile = ~0ull;
-    unsigned long long prev = 0;
-    for (unsigned long long item = blockIdx.x; item < num_items; item += gridDim.x) {
-      const unsigned long long tile = item / p.num_panels;
+    for (unsigned long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      // one evaluation per (thread, tile); every column panel of the tile reuses it
+      const unsigned long long lr = tile * kTileRows + r;
+      const unsigned long long prev = (lr < p.n_local)
+          ? dest_pointer(p.global_offset + lr, p.key, p.plan, p.dst, p.row_pitch)
+          : 0ull;
+      for (uint32_t panel = 0; panel < p.num_panels; ++panel) {
       mbar_wait(&sm.empty[stage], phase ^ 1);
-      if (tile != prev_tile) {
-        const unsigned long long lr = tile * kTileRows + r;
-        prev = (lr < p.n_local)
-            ? dest_pointer(p.global_offset + lr, p.key, p.plan, p.dst, p.row_pitch)
-            : 0ull;
-        prev_tile = tile;
-      }
       sts64(&sm.dptr[stage][r], prev);
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.idx_full[stage]);
+      if (!tmap) {
+        // 1-D bulk path: each index warp loads its share of the panel's columns
+        // (issue is serialised per lane, so spread it over the warps).
+        const uint32_t col0 = panel * PANEL;
+        const uint32_t ncols = min(static_cast<uint32_t>(PANEL), p.num_cols - col0);
+        const uint32_t w = warp - 1;
+        const uint32_t per = (ncols + kIndexWarps - 1) / kIndexWarps;
+        const uint32_t c_lo = min(w * per, ncols), c_hi = min(c_lo + per, ncols);
+        if (lane == 0) mbar_arrive_expect_tx(&sm.full[stage], (c_hi - c_lo) * kTileRows * 4u);
+        __syncwarp();
+        for (uint32_t c = c_lo + lane; c < c_hi; c += 32) {
+          const uint8_t* src = p.cols[col0 + c] + tile * kTileRows * 4ull;
+          tma_load_1d(&sm.tile[stage][c * kPitchWords], src, kTileRows * 4u, &sm.full[stage]);
+        }
+      }
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
     }
   } else {
     // ===== consumers: transpose + cast + scatter =====
@@ -238,9 +270,8 @@ __global__ void __launch_bounds__(kThreads, 1) scatter_tma_kernel(const FastPara
     const int q = lane >> 2;
     int stage = 0;
     uint32_t phase = 0;
-    for (unsigned long long item = blockIdx.x; item < num_items; item += gridDim.x) {
-      const unsigned long long tile = item / p.num_panels;
-      const uint32_t panel = static_cast<uint32_t>(item - tile * p.num_panels);
+    for (unsigned long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+    for (uint32_t panel = 0; panel < p.num_panels; ++panel) {
       const uint32_t col0 = panel * PANEL;
       const uint32_t ncols = min(static_cast<uint32_t>(PANEL), p.num_cols - col0);
       mbar_wait(&sm.idx_full[stage], phase);
@@ -265,8 +296,10 @@ __global__ void __launch_bounds__(kThreads, 1) scatter_tma_kernel(const FastPara
             // column blocks never share a bank group when FPL is a multiple of 8
             const int kk = (FPL >= 8) ? ((k + 4 * (q & 1)) & (FPL - 1)) : k;
             const uint32_t f = f0 + kk;
-            float4 x = (f < ncols) ? lds128(A + f * kPitchWords + rg * 4)
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float* src_word = tmap
+                ? A + (rg >> 3) * (PANEL * kBoxRows) + f * kBoxRows + ((((rg & 7) ^ (f & 7))) << 2)
+                : A + f * kPitchWords + rg * 4;
+            float4 x = (f < ncols) ? lds128(src_word) : make_float4(0.f, 0.f, 0.f, 0.f);
             if (FPL >= 8 && (q & 1)) {
               // undo the rotation with static register indices
               v[(k + 4) & (FPL - 1)][0] = x.x; v[(k + 4) & (FPL - 1)][1] = x.y;
@@ -583,7 +616,7 @@ __global__ void wait_flags_kernel(const uint32_t* flags, uint32_t count, uint32_
 // ---------------------------------------------------------------------------
 template <int MODE>
 static void launch_fast_mode(const FastParams& p, int grid, cudaStream_t stream) {
-  const size_t smem = sizeof(FastSmem<MODE>) + 128;
+  const size_t smem = sizeof(FastSmem<MODE>) + 1024;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(scatter_tma_kernel<MODE>,
@@ -596,6 +629,7 @@ static void launch_fast_mode(const FastParams& p, int grid, cudaStream_t stream)
 }
 
 int fast_panel_cols(int mode) { return mode == 2 ? ModeTraits<2>::PANEL : ModeTraits<0>::PANEL; }
+int fast_ctas_per_sm(int mode) { return mode == 2 ? ModeTraits<2>::MIN_CTAS : ModeTraits<0>::MIN_CTAS; }
 int fast_tile_rows() { return kTileRows; }
 
 void launch_scatter_fast(const FastParams& p, int mode, int grid, cudaStream_t stream) {

@@ -103,7 +103,8 @@ class DeviceShuffleEngine:
                  exchange: str = "p2p", wait_mode: str = "host",
                  flag_timeout_s: float = 300.0, index=None,
                  device_index: Optional[int] = None, grid: Optional[int] = None,
-                 process_group=None, force_generic: bool = False):
+                 process_group=None, force_generic: bool = False,
+                 use_tensor_map: bool = True):
         import torch
         self.C = load_native()
         self.torch = torch
@@ -136,6 +137,7 @@ class DeviceShuffleEngine:
         self.resident, self.exchange, self.wait_mode = resident, exchange, wait_mode
         self.flag_timeout_s = flag_timeout_s
         self.force_generic = force_generic
+        self.use_tensor_map = use_tensor_map
         self.local_trainers: List[int] = ([rank] if world > 1
                                           else list(range(self.plan.num_trainers)))
         self.sm_count = self.C.sm_count(device_index)
@@ -372,8 +374,8 @@ class DeviceShuffleEngine:
     # ------------------------------------------------------------------
     # one epoch
     # ------------------------------------------------------------------
-    def _grid(self, work_items: int) -> int:
-        g = self.grid_override or self.sm_count
+    def _grid(self, work_items: int, ctas_per_sm: int = 1) -> int:
+        g = self.grid_override or self.sm_count * ctas_per_sm
         return max(1, min(g, work_items))
 
     def _launch_chunk(self, key_words, buf: int, n_rows: int, global_offset: int,
@@ -383,15 +385,24 @@ class DeviceShuffleEngine:
             return
         if self.fast_mode >= 0:
             ncols = len(self.fast_field_idx)
-            panels = -(-ncols // C.fast_panel_cols(self.fast_mode))
             tiles = -(-n_rows // C.TILE_ROWS)
+            # fast columns are contiguous with one stride: hand the kernel a 2-D
+            # tensor map (4 TMA box loads per tile instead of 64 bulk copies)
+            ptrs = self.src_col_ptrs[buf]
+            stride = self.col_bytes[0]
+            uniform = (self.use_tensor_map and all(
+                ptrs[i] == ptrs[0] + i * stride for i in range(ncols)))
             C.scatter_fast(key=key_words, num_rows=plan.num_rows,
                            num_trainers=plan.num_trainers, cols=self.fast_cols_dev[buf],
                            num_cols=ncols, n_local=n_rows, global_offset=global_offset,
                            row_pitch=lay.row_pitch,
                            scale_offset=max(0, lay.scale_offset), dst=dst,
-                           mode=self.fast_mode, grid=self._grid(tiles * panels),
-                           stream=self.shuffle_stream)
+                           mode=self.fast_mode,
+                           grid=self._grid(tiles, C.fast_ctas_per_sm(self.fast_mode)),
+                           stream=self.shuffle_stream,
+                           col_base=ptrs[0] if uniform else 0,
+                           col_stride=stride if uniform else 0,
+                           rows_alloc=(stride // 4) if uniform else 0)
             self.launches += 1
         if self.generic_field_idx:
             lo, hi = self.generic_range

@@ -157,6 +157,19 @@ def test_generic_casts_match_golden(small_dataset):
         dev.close(); cpu.close()
 
 
+def test_one_d_bulk_path_matches_golden(tmp_path_factory):
+    """use_tensor_map=False: the cp.async.bulk (UBLKCP) path for arbitrary
+    column pointers must agree with the tensor-map (UTMALDG) path."""
+    files = _float_files(tmp_path_factory, 70, name="o")
+    cols = [f"f{i}" for i in range(69)] + ["labels"]
+    cpu, dev = _engines(files, _f32_layout(cols), 2, use_tensor_map=False)
+    assert dev.fast_mode == 0
+    try:
+        _compare_epochs(cpu, dev, epochs=(0, 1))
+    finally:
+        dev.close(); cpu.close()
+
+
 def test_forced_generic_equals_fast(tmp_path_factory):
     files = _float_files(tmp_path_factory, 64, name="g")
     cols = [f"f{i}" for i in range(63)] + ["labels"]

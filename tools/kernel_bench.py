@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--verify", action="store_true")
+    ap.add_argument("--no-tmap", action="store_true", help="use 1-D bulk copies")
     a = ap.parse_args()
     torch.cuda.set_device(0)
     _C.set_device(0)
@@ -63,11 +64,15 @@ def main():
                                write_lo=0, write_hi=pitch, dst=dst_ptrs,
                                grid=a.grid or sm * 2, stream=stream)
         else:
-            tiles = -(-n // _C.TILE_ROWS) * -(-F // _C.fast_panel_cols(a.mode))
+            tiles = -(-n // _C.TILE_ROWS)
             _C.scatter_fast(key=key, num_rows=n, num_trainers=T, cols=ptrs.data_ptr(),
                             num_cols=F, n_local=n, global_offset=0, row_pitch=pitch,
                             scale_offset=scale_off, dst=dst_ptrs, mode=a.mode,
-                            grid=min(a.grid or sm, tiles), stream=stream)
+                            grid=min(a.grid or sm * _C.fast_ctas_per_sm(a.mode), tiles),
+                            stream=stream,
+                            col_base=0 if a.no_tmap else src.data_ptr(),
+                            col_stride=0 if a.no_tmap else rows_pad * 4,
+                            rows_alloc=0 if a.no_tmap else rows_pad)
     for i in range(a.warmup):
         launch(i)
     torch.cuda.synchronize()
