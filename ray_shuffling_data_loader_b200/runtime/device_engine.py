@@ -41,6 +41,7 @@ from ray_shuffling_data_loader_b200.parallel import bootstrap
 from ray_shuffling_data_loader_b200.runtime import ingest
 from ray_shuffling_data_loader_b200.runtime.chunks import EpochBuffer
 from ray_shuffling_data_loader_b200 import stats as stats_mod
+from ray_shuffling_data_loader_b200.utils import trace
 
 
 def load_native():
@@ -337,10 +338,28 @@ class DeviceShuffleEngine:
                     self.stats.map_start(epoch)
             self._pinned: List[int] = []
 
+            # One pinned block, bump-allocated: same-shape columns end up with a
+            # uniform stride, so a whole chunk moves with ONE cudaMemcpy2DAsync.
+            dtypes = {f.name: np.dtype(L.numpy_storage_dtype(f.src_code)) for f in self.src_fields}
+            widths = {f.name: f.width for f in self.src_fields}
+            total = sum(_align(self.n_local * dtypes[n].itemsize * max(1, widths[n]))
+                        for n in dict.fromkeys(f.name for f in self.src_fields)) + 4096
+            host_block, host_ptr = pinned_array(C, (total,), np.uint8)
+            self._pinned.append(host_ptr)
+            cursor = {"off": 0}
+            bump_lock = threading.Lock()
+
             def alloc(shape, dt):
-                arr, ptr = pinned_array(C, shape, dt)
-                self._pinned.append(ptr)
-                return arr
+                dt = np.dtype(dt)
+                nbytes = int(np.prod(shape)) * dt.itemsize
+                with bump_lock:
+                    off = cursor["off"]
+                    if off + nbytes > total:        # unexpected shape: private block
+                        arr, ptr = pinned_array(C, shape, dt)
+                        self._pinned.append(ptr)
+                        return arr
+                    cursor["off"] = off + _align(nbytes)
+                return host_block[off:off + nbytes].view(dt).reshape(shape)
 
             names = [f.name for f in self.src_fields]
             table = ingest.load_table(self.index, self.src_lo, self.src_lo + self.n_local,
@@ -424,13 +443,15 @@ class DeviceShuffleEngine:
         C, plan = self.C, self.plan
         C.set_device(self.device_index)      # driver thread: device is per-thread
         self.torch.cuda.set_device(self.device_index)
-        self._ensure_ingested(epoch)
+        with trace.span("ingest", epoch=epoch):
+            self._ensure_ingested(epoch)
         slot = epoch % self.window
         if epoch >= self.window:
             # Back-pressure: every trainer must have released this slot's
             # previous epoch before any source may overwrite it.
-            lag = self._poll(self._consumed_ptr(self.rank, 0), plan.num_trainers,
-                             epoch - self.window + 1, self.flag_timeout_s)
+            with trace.span("backpressure_wait", epoch=epoch):
+                lag = self._poll(self._consumed_ptr(self.rank, 0), plan.num_trainers,
+                                 epoch - self.window + 1, self.flag_timeout_s)
             if lag >= 0:
                 raise TimeoutError(
                     f"trainer {lag} did not release epoch {epoch - self.window} within "
@@ -443,6 +464,7 @@ class DeviceShuffleEngine:
         dst = [self._slot_ptr(slot, t) for t in range(plan.num_trainers)]
         ev0, ev1 = C.event_create(True), C.event_create(True)
         C.event_record(ev0, self.shuffle_stream)
+        trace.instant("launch_epoch_shuffle", epoch=epoch, slot=slot)
         if self.exchange == "nccl":
             from ray_shuffling_data_loader_b200.parallel import nccl_baseline
             nccl_baseline.exchange_epoch(self, key_words, slot)
@@ -478,15 +500,39 @@ class DeviceShuffleEngine:
             b = k % self.num_src_bufs
             if self._buf_used[b]:
                 C.stream_wait_event(self.copy_stream, self.buf_free[b])
-            for f, ptr, col in zip(self.src_fields, self.src_col_ptrs[b], self.host_cols):
-                part = col[row0:row0 + rows]
-                C.memcpy_async(ptr, part.ctypes.data, part.nbytes, C.H2D, self.copy_stream)
+            self._h2d_chunk(b, row0, rows)
             C.event_record(self.h2d_done[b], self.copy_stream)
             C.stream_wait_event(self.shuffle_stream, self.h2d_done[b])
             self._launch_chunk(key_words, b, rows, self.src_lo + row0, dst)
             C.event_record(self.buf_free[b], self.shuffle_stream)
             self._buf_used[b] = True
             k += 1
+
+    def _h2d_chunk(self, b: int, row0: int, rows: int):
+        """Copy rows [row0, row0+rows) of every source column into staging buffer
+        ``b``: runs of columns with a uniform host stride go as one 2-D copy."""
+        C = self.C
+        ptrs, cols, fields = self.src_col_ptrs[b], self.host_cols, self.src_fields
+        i, n = 0, len(fields)
+        while i < n:
+            isz = L.itemsize(fields[i].src_code) * fields[i].width
+            base = cols[i].ctypes.data
+            j = i + 1
+            if j < n:
+                hstride = cols[j].ctypes.data - base
+                dstride = ptrs[j] - ptrs[i]
+                while (j < n and hstride > 0 and dstride > 0
+                       and L.itemsize(fields[j].src_code) * fields[j].width == isz
+                       and cols[j].ctypes.data - base == (j - i) * hstride
+                       and ptrs[j] - ptrs[i] == (j - i) * dstride):
+                    j += 1
+            if j - i >= 2:
+                C.memcpy2d_async(ptrs[i], dstride, base + row0 * isz, hstride, rows * isz,
+                                 j - i, C.H2D, self.copy_stream)
+            else:
+                j = i + 1
+                C.memcpy_async(ptrs[i], base + row0 * isz, rows * isz, C.H2D, self.copy_stream)
+            i = j
 
     def h2d_bytes_per_epoch(self) -> int:
         if self.resident != "host":
@@ -526,8 +572,9 @@ class DeviceShuffleEngine:
                 self.launches += 1
             else:
                 limit = self.flag_timeout_s if timeout is None else timeout
-                lag = self._poll(self._produced_ptr(self.rank, slot, 0), self.world,
-                                 epoch + 1, limit)
+                with trace.span("wait_epoch_produced", epoch=epoch):
+                    lag = self._poll(self._produced_ptr(self.rank, slot, 0), self.world,
+                                     epoch + 1, limit)
                 if lag >= 0:
                     raise TimeoutError(
                         f"source rank {lag} did not deliver epoch {epoch} within {limit}s")

@@ -1,0 +1,10 @@
+#!/bin/bash
+# Race / memory checking of the kernels (the reference has none).
+# Run on a GPU box: tools/sanitize.sh [memcheck|racecheck|synccheck]
+set -euo pipefail
+cd "$(dirname "$0")/.."
+tool="${1:-memcheck}"
+compute-sanitizer --tool "$tool" --error-exitcode 1 \
+  python tools/kernel_bench.py --rows 200000 --cols 64 --mode 0 --iters 1 --warmup 1 --verify
+compute-sanitizer --tool "$tool" --error-exitcode 1 \
+  python tools/kernel_bench.py --rows 200000 --cols 64 --mode 3 --iters 1 --warmup 1 --verify
