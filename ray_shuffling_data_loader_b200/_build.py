@@ -45,6 +45,31 @@ def _run(cmd: List[str], verbose: bool):
         print(res.stdout, res.stderr)
 
 
+def build_variant(name: str, defines: List[str], verbose: bool = False) -> str:
+    """Build an experimental variant of the extension (different -D tile
+    geometry) into ``csrc/build/variants/<name>/_C*.so`` for A/B kernel runs
+    (``tools/kernel_bench.py --ext``)."""
+    import pybind11
+    out_dir = os.path.join(BUILD_DIR, "variants", name)
+    os.makedirs(out_dir, exist_ok=True)
+    target = os.path.join(out_dir, "_C" + sysconfig.get_config_var("EXT_SUFFIX"))
+    nvcc = os.path.join(CUDA_HOME, "bin", "nvcc")
+    includes = ["-I", CSRC, "-I", pybind11.get_include(),
+                "-I", sysconfig.get_paths()["include"],
+                "-I", os.path.join(CUDA_HOME, "include")]
+    objs = []
+    for src in CU_SOURCES:
+        obj = os.path.join(out_dir, src + ".o")
+        _run([nvcc, "-std=c++17", "-O3", *ARCH_FLAGS, "-lineinfo", *[f"-D{d}" for d in defines],
+              "-Xcompiler", "-fPIC", *includes, "-c", os.path.join(CSRC, src), "-o", obj], verbose)
+        objs.append(obj)
+    # the bindings object is geometry independent: reuse the main build's
+    objs.append(os.path.join(BUILD_DIR, CPP_SOURCES[0] + ".o"))
+    _run(["g++", "-shared", "-o", target, *objs, "-L", os.path.join(CUDA_HOME, "lib64"),
+          "-lcudart_static", "-lpthread", "-ldl", "-lrt"], verbose)
+    return target
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     import pybind11
     os.makedirs(BUILD_DIR, exist_ok=True)

@@ -234,7 +234,8 @@ class FlagPoller {
 PYBIND11_MODULE(_C, m) {
   m.doc() = "ray_shuffling_data_loader_b200 native runtime (sm_100a)";
   m.attr("MAX_TRAINERS") = RSDL_MAX_TRAINERS;
-  m.attr("TILE_ROWS") = rsdl::fast_tile_rows();
+  m.attr("TILE_ROWS") = rsdl::fast_max_tile_rows();   // source-column padding granule
+  m.def("fast_tile_rows", &rsdl::fast_tile_rows);
   m.def("fast_panel_cols", &rsdl::fast_panel_cols);
 
   // ---- device -----------------------------------------------------------

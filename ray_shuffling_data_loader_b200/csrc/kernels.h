@@ -55,7 +55,8 @@ struct FlagTargets {
 
 int fast_panel_cols(int mode);
 int fast_ctas_per_sm(int mode);
-int fast_tile_rows();
+int fast_tile_rows(int mode);
+int fast_max_tile_rows();
 
 void launch_scatter_fast(const FastParams& p, int mode, int grid, cudaStream_t stream);
 void launch_scatter_generic(GenericParams p, int grid, cudaStream_t stream);

@@ -32,6 +32,17 @@
 #include "kernels.h"
 #include "perm.cuh"
 
+// Tile geometry of the f32/bf16 fast path (overridable for experiments).
+#ifndef RSDL_TILE_F32
+#define RSDL_TILE_F32 256
+#endif
+#ifndef RSDL_STAGES_F32
+#define RSDL_STAGES_F32 3
+#endif
+#ifndef RSDL_CTAS_F32
+#define RSDL_CTAS_F32 1
+#endif
+
 namespace rsdl {
 
 // ---------------------------------------------------------------------------
@@ -149,16 +160,18 @@ dest_pointer(unsigned long long gi, const PermKeyDev& key, const PlanDev& plan,
 // their columns rotated by 4), so every shared load is conflict free, the 4x4
 // transposition happens in registers with static indexing, and each store
 // instruction writes, for 4 different rows, one full 128-byte line of the row.
-constexpr int kTileRows = 128;
-constexpr int kPitchWords = kTileRows + 4;   // shared-memory words per column
 constexpr int kConsumerWarps = 8;
-constexpr int kIndexWarps = kTileRows / 32;   // one destination pointer per thread per tile
-constexpr int kThreads = 32 * (1 + kIndexWarps + kConsumerWarps);
+constexpr int kMaxTileRows = 256;
 
 template <int MODE> struct ModeTraits;
-template <> struct ModeTraits<0> { static constexpr int FPL = 4;  static constexpr int PANEL = 64;  static constexpr int STAGES = 3; static constexpr int MIN_CTAS = 2; };
-template <> struct ModeTraits<1> { static constexpr int FPL = 8;  static constexpr int PANEL = 64;  static constexpr int STAGES = 3; static constexpr int MIN_CTAS = 2; };
-template <> struct ModeTraits<2> { static constexpr int FPL = 16; static constexpr int PANEL = 128; static constexpr int STAGES = 3; static constexpr int MIN_CTAS = 1; };
+// TILE rows per tile: 256 makes every 1-D bulk copy 1 KB (the TMA unit retires
+// roughly one op per ~46 cycles per SM, so 512-byte copies cap the read rate near
+// 3 TB/s); INDEX_WARPS x 32 threads each own TILE/(32*INDEX_WARPS) rows' pointers.
+template <> struct ModeTraits<0> { static constexpr int FPL = 4;  static constexpr int PANEL = 64;  static constexpr int TILE = RSDL_TILE_F32; static constexpr int STAGES = RSDL_STAGES_F32; static constexpr int MIN_CTAS = RSDL_CTAS_F32; };
+template <> struct ModeTraits<1> { static constexpr int FPL = 8;  static constexpr int PANEL = 64;  static constexpr int TILE = RSDL_TILE_F32; static constexpr int STAGES = RSDL_STAGES_F32; static constexpr int MIN_CTAS = RSDL_CTAS_F32; };
+template <> struct ModeTraits<2> { static constexpr int FPL = 16; static constexpr int PANEL = 128; static constexpr int TILE = 128; static constexpr int STAGES = 3; static constexpr int MIN_CTAS = 1; };
+constexpr int kIndexWarps = 4;
+constexpr int kThreads = 32 * (1 + kIndexWarps + kConsumerWarps);
 
 // Two shared-memory tile layouts (both conflict-free for the consumers):
 //  * tensor-map path: kTileRows/32 TMA boxes of [PANEL cols][32 rows] with the
@@ -166,15 +179,16 @@ template <> struct ModeTraits<2> { static constexpr int FPL = 16; static constex
 //    b*PANEL*128 + c*128 + (((r%32)/4 ^ (c&7)) << 4) + (r%4)*4 bytes;
 //  * 1-D bulk path (arbitrary column pointers): column c at word c*kPitchWords.
 constexpr int kBoxRows = 32;
-constexpr int kBoxesPerTile = kTileRows / kBoxRows;
 
 template <int MODE>
 struct alignas(1024) FastSmem {
   static constexpr int PANEL = ModeTraits<MODE>::PANEL;
   static constexpr int STAGES = ModeTraits<MODE>::STAGES;
+  static constexpr int TILE = ModeTraits<MODE>::TILE;
+  static constexpr int kPitchWords = TILE + 4;   // 1-D path: words per column
   static constexpr int kTileWords = ((PANEL * kPitchWords + 255) / 256) * 256;
   float tile[STAGES][kTileWords];
-  unsigned long long dptr[STAGES][kTileRows];
+  unsigned long long dptr[STAGES][TILE];
   uint64_t full[STAGES];       // TMA bytes landed
   uint64_t idx_full[STAGES];   // destination pointers written
   uint64_t empty[STAGES];      // consumers done with the stage
@@ -187,6 +201,10 @@ scatter_tma_kernel(const __grid_constant__ FastParams p) {
   constexpr int FPL = T::FPL;
   constexpr int PANEL = T::PANEL;
   constexpr int STAGES = T::STAGES;
+  constexpr int kTileRows = T::TILE;
+  constexpr int kPitchWords = kTileRows + 4;
+  constexpr int kBoxesPerTile = kTileRows / kBoxRows;
+  constexpr int kRowsPerIndexThread = kTileRows / (32 * kIndexWarps);
   constexpr int PASSES = PANEL / (8 * FPL);
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment: the 128-byte TMA swizzle is a function of address bits
@@ -231,18 +249,24 @@ scatter_tma_kernel(const __grid_constant__ FastParams p) {
     // ===== index warps: the tile's shared permutation index =====
     // One Feistel evaluation per thread per tile, running STAGES tiles ahead of
     // the consumers; column panels of the same rows reuse the previous result.
-    const int r = threadIdx.x - 32;            // row inside the tile
+    const int r = threadIdx.x - 32;            // first row owned inside the tile
     int stage = 0;
     uint32_t phase = 0;
     for (unsigned long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      // one evaluation per (thread, tile); every column panel of the tile reuses it
-      const unsigned long long lr = tile * kTileRows + r;
-      const unsigned long long prev = (lr < p.n_local)
-          ? dest_pointer(p.global_offset + lr, p.key, p.plan, p.dst, p.row_pitch)
-          : 0ull;
+      // evaluated once per (row, tile); every column panel of the tile reuses it
+      unsigned long long prev[kRowsPerIndexThread];
+#pragma unroll
+      for (int i = 0; i < kRowsPerIndexThread; ++i) {
+        const unsigned long long lr = tile * kTileRows + r + i * (32 * kIndexWarps);
+        prev[i] = (lr < p.n_local)
+            ? dest_pointer(p.global_offset + lr, p.key, p.plan, p.dst, p.row_pitch)
+            : 0ull;
+      }
       for (uint32_t panel = 0; panel < p.num_panels; ++panel) {
       mbar_wait(&sm.empty[stage], phase ^ 1);
-      sts64(&sm.dptr[stage][r], prev);
+#pragma unroll
+      for (int i = 0; i < kRowsPerIndexThread; ++i)
+        sts64(&sm.dptr[stage][r + i * (32 * kIndexWarps)], prev[i]);
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.idx_full[stage]);
       if (!tmap) {
@@ -630,7 +654,8 @@ static void launch_fast_mode(const FastParams& p, int grid, cudaStream_t stream)
 
 int fast_panel_cols(int mode) { return mode == 2 ? ModeTraits<2>::PANEL : ModeTraits<0>::PANEL; }
 int fast_ctas_per_sm(int mode) { return mode == 2 ? ModeTraits<2>::MIN_CTAS : ModeTraits<0>::MIN_CTAS; }
-int fast_tile_rows() { return kTileRows; }
+int fast_tile_rows(int mode) { return mode == 2 ? ModeTraits<2>::TILE : ModeTraits<0>::TILE; }
+int fast_max_tile_rows() { return kMaxTileRows; }
 
 void launch_scatter_fast(const FastParams& p, int mode, int grid, cudaStream_t stream) {
   if (p.n_local == 0) return;

@@ -59,6 +59,9 @@ class CpuShuffleEngine:
         self._ingest_reads: List[float] = []
         self._bytes_in_flight = 0
         self._closed = False
+        from ray_shuffling_data_loader_b200 import stats as stats_mod
+        self._bytes_fn = self.bytes_in_use
+        stats_mod.register_bytes_used_source(self._bytes_fn)
 
     # -- ingest -------------------------------------------------------------
     def _ensure_ingested(self, epoch: int):
@@ -165,5 +168,7 @@ class CpuShuffleEngine:
     def close(self):
         if not self._closed:
             self._closed = True
+            from ray_shuffling_data_loader_b200 import stats as stats_mod
+            stats_mod.unregister_bytes_used_source(self._bytes_fn)
             self._pool.shutdown(wait=True)
             self._packed = None

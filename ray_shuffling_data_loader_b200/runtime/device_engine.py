@@ -404,7 +404,7 @@ class DeviceShuffleEngine:
             return
         if self.fast_mode >= 0:
             ncols = len(self.fast_field_idx)
-            tiles = -(-n_rows // C.TILE_ROWS)
+            tiles = -(-n_rows // C.fast_tile_rows(self.fast_mode))
             # fast columns are contiguous with one stride: hand the kernel a 2-D
             # tensor map (4 TMA box loads per tile instead of 64 bulk copies)
             ptrs = self.src_col_ptrs[buf]

@@ -15,8 +15,21 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 
-from ray_shuffling_data_loader_b200 import _C
 from ray_shuffling_data_loader_b200.ops import perm
+
+_C = None
+
+
+def load_ext(path):
+    global _C
+    if path:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("_C", path)
+        _C = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(_C)
+    else:
+        from ray_shuffling_data_loader_b200 import _C as mod
+        _C = mod
 
 
 def main():
@@ -30,7 +43,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--verify", action="store_true")
     ap.add_argument("--no-tmap", action="store_true", help="use 1-D bulk copies")
+    ap.add_argument("--ext", default=None, help="path to an alternative _C build")
+    ap.add_argument("--tag", default="")
     a = ap.parse_args()
+    load_ext(a.ext)
     torch.cuda.set_device(0)
     _C.set_device(0)
     sm = _C.sm_count(0)
@@ -64,7 +80,7 @@ def main():
                                write_lo=0, write_hi=pitch, dst=dst_ptrs,
                                grid=a.grid or sm * 2, stream=stream)
         else:
-            tiles = -(-n // _C.TILE_ROWS)
+            tiles = -(-n // _C.fast_tile_rows(a.mode))
             _C.scatter_fast(key=key, num_rows=n, num_trainers=T, cols=ptrs.data_ptr(),
                             num_cols=F, n_local=n, global_offset=0, row_pitch=pitch,
                             scale_offset=scale_off, dst=dst_ptrs, mode=a.mode,
@@ -102,7 +118,8 @@ def main():
             os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    out = {"rows": n, "cols": F, "mode": a.mode, "trainers": T, "row_pitch": pitch,
+    out = {"tag": a.tag, "tmap": not a.no_tmap, "tile_rows": _C.fast_tile_rows(a.mode) if a.mode < 3 else 0,
+           "rows": n, "cols": F, "mode": a.mode, "trainers": T, "row_pitch": pitch,
            "ms_best": best, "ms_median": med, "gbps_best": bytes_moved / best / 1e6,
            "gbps_median": bytes_moved / med / 1e6, "bytes": bytes_moved, "grid": a.grid or sm}
     if peaks.get("hbm_gbs"):
