@@ -167,6 +167,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------
 
 def run_phase(ds, engine, torch, dist, world, steps, warmup, batch_size, d2h_each_step):
+    row_pitch = engine.layout.row_pitch
     """Consume warmup + steps batches; returns (max-over-ranks device ms, wall s,
     launches in the timed region, checksum)."""
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -180,7 +181,7 @@ def run_phase(ds, engine, torch, dist, world, steps, warmup, batch_size, d2h_eac
     checksum = 0.0
     while done < total:
         ds.set_epoch(epoch)
-        for packed in ds:
+        for features, label in ds:      # the public API: (features[B, F-1], label[B, 1])
             if done == warmup:
                 torch.cuda.synchronize()
                 if world > 1:
@@ -189,8 +190,11 @@ def run_phase(ds, engine, torch, dist, world, steps, warmup, batch_size, d2h_eac
                 launches0 = engine.launches
                 wall0 = time.perf_counter()
                 ev0.record()
-            # consume: every byte of the batch is read by our reduction kernel
-            engine.batch_sum_all(packed, acc)
+            # consume: every byte of the batch (features + label share one packed
+            # row; the feature view starts at the batch's first byte) is read by
+            # our reduction kernel
+            base = features[0] if isinstance(features, tuple) else features
+            engine.batch_sum_all(base, acc, nbytes=base.shape[0] * row_pitch)
             if d2h_each_step:
                 host_acc.copy_(acc, non_blocking=True)
                 torch.cuda.current_stream().synchronize()
@@ -217,21 +221,21 @@ def run_phase(ds, engine, torch, dist, world, steps, warmup, batch_size, d2h_eac
 
 
 def make_dataset(args, files, rank, world, epochs, resident, torch, seed=20260921):
-    from ray_shuffling_data_loader_b200 import ShufflingDataset
-    from ray_shuffling_data_loader_b200.ops import layout as L
-    cols = [f"f{i}" for i in range(args.cols - 1)] + ["labels"]
-    dst = {"float32": L.DT_F32, "bfloat16": L.DT_BF16, "fp8": L.DT_FP8}[args.feature_dtype]
-
-    def layout_fn(schema):
-        return L.build_layout([(c, schema[c][0], dst, 1) for c in cols],
-                              fp8_block_scale=(dst == L.DT_FP8))
+    """The flagship public API, exactly as a user would call it."""
+    from ray_shuffling_data_loader_b200 import TorchShufflingDataset
+    feature_columns = [f"f{i}" for i in range(args.cols - 1)]
+    dt = {"float32": torch.float32, "bfloat16": torch.bfloat16,
+          "fp8": getattr(torch, "float8_e4m3fn", None)}[args.feature_dtype]
     opts = dict(resident=resident, exchange=args.exchange)
     if resident == "host":
         opts["stream_chunk_rows"] = args.batch_size
-    return ShufflingDataset(files, epochs, world, args.batch_size, rank, num_reducers=world,
-                            max_concurrent_epochs=2, seed=seed, backend="cuda",
-                            output="packed", layout_fn=layout_fn,
-                            queue_name=f"bench-{resident}", **opts)
+    fp8 = args.feature_dtype == "fp8"
+    return TorchShufflingDataset(
+        files, epochs, world, args.batch_size, rank, num_reducers=world,
+        max_concurrent_epochs=2, feature_columns=feature_columns,
+        feature_types=[dt] * len(feature_columns), label_column="labels",
+        label_type=dt if not fp8 else torch.float32, packed_features=True,
+        fp8_block_scale=fp8, seed=seed, backend="cuda", queue_name=f"bench-{resident}", **opts)
 
 
 def run_ours(args):
@@ -257,7 +261,7 @@ def run_ours(args):
     # ---- device-timed, HBM-resident -----------------------------------------
     t0 = time.perf_counter()
     ds = make_dataset(args, files, rank, world, epochs, "hbm", torch)
-    engine = ds.engine
+    engine = ds.dataset.engine
     if sampler:
         sampler.start()
     ms, wall, launches, chk = run_phase(ds, engine, torch, dist, world, args.steps, args.warmup,
@@ -267,7 +271,7 @@ def run_ours(args):
     kernel_ms = [engine.epoch_kernel_ms(e) for e in range(epochs) if engine.epoch_kernel_ms(e)]
     fast_mode = engine.fast_mode
     row_pitch = engine.layout.row_pitch
-    ds.close()
+    ds.dataset.close()
     rows = args.steps * args.batch_size * world
     value = rows / (ms / 1e3)
 
@@ -275,11 +279,11 @@ def run_ours(args):
     e2e = None
     if not args.skip_e2e:
         ds2 = make_dataset(args, files, rank, world, epochs, "host", torch)
-        eng2 = ds2.engine
+        eng2 = ds2.dataset.engine
         ms2, wall2, launches2, chk2 = run_phase(ds2, eng2, torch, dist, world, args.steps,
                                                 args.warmup, args.batch_size, d2h_each_step=True)
         h2d_epoch = eng2.h2d_bytes_per_epoch()
-        ds2.close()
+        ds2.dataset.close()
         e2e = {"value": rows / wall2, "unit": "rows/s",
                "h2d_bytes_per_step": int(h2d_epoch / batches_per_epoch),
                "d2h_bytes_per_step": 8, "ms_per_step": wall2 * 1e3 / args.steps,

@@ -85,14 +85,16 @@ EncodeTiledFn encode_tiled_fn() {
 // 2-D view [num_cols][rows_alloc] of 4-byte source columns with a uniform
 // stride; boxes are [panel cols][32 rows] = 128-byte rows, 128-byte swizzle.
 void make_source_tmap(CUtensorMap* map, uintptr_t base, uint64_t rows_alloc, uint32_t num_cols,
-                      uint64_t col_stride_bytes, uint32_t panel_cols) {
+                      uint64_t col_stride_bytes, uint32_t panel_cols, uint32_t box_rows,
+                      bool swizzle) {
   cuuint64_t dims[2] = {rows_alloc, num_cols};
   cuuint64_t strides[1] = {col_stride_bytes};
-  cuuint32_t box[2] = {32, panel_cols};
+  cuuint32_t box[2] = {box_rows, panel_cols};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = encode_tiled_fn()(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2,
                                  reinterpret_cast<void*>(base), dims, strides, box, estr,
-                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -344,14 +346,18 @@ PYBIND11_MODULE(_C, m) {
            uintptr_t cols, uint32_t num_cols, uint64_t n_local, uint64_t global_offset,
            uint32_t row_pitch, uint32_t scale_offset, const std::vector<uintptr_t>& dst, int mode,
            int grid, uintptr_t stream, uintptr_t col_base, uint64_t col_stride,
-           uint64_t rows_alloc) {
+           uint64_t rows_alloc, int tmap_mode) {
           FastParams p;
           std::memset(&p.tmap, 0, sizeof(p.tmap));
           p.use_tmap = 0;
-          if (col_base != 0 && col_stride % 16 == 0 && rows_alloc % 32 == 0) {
+          const uint32_t tile_rows = static_cast<uint32_t>(rsdl::fast_tile_rows(mode));
+          if (tmap_mode != 0 && col_base != 0 && col_stride % 16 == 0 &&
+              rows_alloc % tile_rows == 0) {
+            const bool dense = tmap_mode == 2;
             make_source_tmap(&p.tmap, col_base, rows_alloc, num_cols, col_stride,
-                             static_cast<uint32_t>(rsdl::fast_panel_cols(mode)));
-            p.use_tmap = 1;
+                             static_cast<uint32_t>(rsdl::fast_panel_cols(mode)),
+                             dense ? tile_rows : 32u, !dense);
+            p.use_tmap = dense ? 2 : 1;
           }
           p.key = make_key(key);
           p.plan = make_plan(num_rows, num_trainers);
@@ -370,7 +376,7 @@ PYBIND11_MODULE(_C, m) {
         py::arg("num_cols"), py::arg("n_local"), py::arg("global_offset"), py::arg("row_pitch"),
         py::arg("scale_offset"), py::arg("dst"), py::arg("mode"), py::arg("grid"),
         py::arg("stream"), py::arg("col_base") = 0, py::arg("col_stride") = 0,
-        py::arg("rows_alloc") = 0);
+        py::arg("rows_alloc") = 0, py::arg("tmap_mode") = 2);
   m.def("fast_ctas_per_sm", &rsdl::fast_ctas_per_sm);
   m.def("scatter_generic",
         [](const std::vector<uint64_t>& key, uint64_t num_rows, uint32_t num_trainers,

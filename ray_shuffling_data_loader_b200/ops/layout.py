@@ -177,7 +177,10 @@ def build_layout(columns: Sequence[Tuple[str, int, int, int]],
         # 16-aligned so the kernel's 16-byte payload stores never touch a scale
         scale_offset = _align(off, 16)
         off = scale_offset + (nelem + 31) // 32
-    return RowLayout(tuple(fields), max(16, _align(off, 16)), scale_offset)
+    # Rows are scattered one at a time: keep every row on its own 32-byte DRAM
+    # sectors (no read-modify-write of a sector shared with a neighbour row).
+    pitch = _align(off, 16) if off <= 16 else _align(off, 32)
+    return RowLayout(tuple(fields), max(16, pitch), scale_offset)
 
 
 def dataframe_layout(schema: Dict[str, Tuple[int, int]]) -> RowLayout:

@@ -139,6 +139,10 @@ class DeviceShuffleEngine:
         self.flag_timeout_s = flag_timeout_s
         self.force_generic = force_generic
         self.use_tensor_map = use_tensor_map
+        # Source tile loads: 0 = 1-D bulk copies (cp.async.bulk, fastest measured:
+        # 512-byte contiguous DRAM reads), 1 = tensor-map boxes with 128B swizzle,
+        # 2 = one dense tensor-map box per tile. See profiles/README.md.
+        self.tmap_mode = int(os.environ.get("RSDL_TMAP_MODE", "0"))
         self.local_trainers: List[int] = ([rank] if world > 1
                                           else list(range(self.plan.num_trainers)))
         self.sm_count = self.C.sm_count(device_index)
@@ -364,7 +368,8 @@ class DeviceShuffleEngine:
             names = [f.name for f in self.src_fields]
             table = ingest.load_table(self.index, self.src_lo, self.src_lo + self.n_local,
                                       columns=list(dict.fromkeys(names)),
-                                      num_threads=self.num_threads, alloc=alloc)
+                                      num_threads=self.num_threads, alloc=alloc,
+                                      copy_fn=self._host_copy)
             self.host_table = table
             self.host_cols = [table.columns[f.name] for f in self.src_fields]
             for f, col in zip(self.src_fields, self.host_cols):
@@ -409,7 +414,7 @@ class DeviceShuffleEngine:
             # tensor map (4 TMA box loads per tile instead of 64 bulk copies)
             ptrs = self.src_col_ptrs[buf]
             stride = self.col_bytes[0]
-            uniform = (self.use_tensor_map and all(
+            uniform = (self.use_tensor_map and self.tmap_mode != 0 and all(
                 ptrs[i] == ptrs[0] + i * stride for i in range(ncols)))
             C.scatter_fast(key=key_words, num_rows=plan.num_rows,
                            num_trainers=plan.num_trainers, cols=self.fast_cols_dev[buf],
@@ -421,7 +426,8 @@ class DeviceShuffleEngine:
                            stream=self.shuffle_stream,
                            col_base=ptrs[0] if uniform else 0,
                            col_stride=stride if uniform else 0,
-                           rows_alloc=(stride // 4) if uniform else 0)
+                           rows_alloc=(stride // 4) if uniform else 0,
+                           tmap_mode=self.tmap_mode)
             self.launches += 1
         if self.generic_field_idx:
             lo, hi = self.generic_range
@@ -507,6 +513,10 @@ class DeviceShuffleEngine:
             C.event_record(self.buf_free[b], self.shuffle_stream)
             self._buf_used[b] = True
             k += 1
+
+    def _host_copy(self, dst: np.ndarray, src: np.ndarray):
+        """Decoded Arrow buffer -> pinned staging on the C++ worker pool."""
+        self.host_pool.parallel_memcpy(dst.ctypes.data, src.ctypes.data, src.nbytes)
 
     def _h2d_chunk(self, b: int, row0: int, rows: int):
         """Copy rows [row0, row0+rows) of every source column into staging buffer
@@ -656,11 +666,14 @@ class DeviceShuffleEngine:
         self.launches += 1
         return out
 
-    def batch_sum_all(self, packed, out):
+    def batch_sum_all(self, packed, out, nbytes: Optional[int] = None):
         """fp64 sum of every fp32 word of a packed fp32 batch, accumulated into
-        ``out`` (1-element float64 CUDA tensor) on the current stream."""
-        self.C.batch_sum_all_f32(packed.data_ptr(), packed.shape[0] * packed.shape[1],
-                                 out.data_ptr(),
+        ``out`` (1-element float64 CUDA tensor) on the current stream. ``packed``
+        is the batch's byte matrix, or any view that starts at the batch's first
+        byte together with ``nbytes`` (e.g. the ``packed_features`` matrix)."""
+        if nbytes is None:
+            nbytes = packed.shape[0] * packed.shape[1] * packed.element_size()
+        self.C.batch_sum_all_f32(packed.data_ptr(), nbytes, out.data_ptr(),
                                  self.torch.cuda.current_stream().cuda_stream)
         self.launches += 1
         return out

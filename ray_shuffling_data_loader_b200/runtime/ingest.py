@@ -121,13 +121,16 @@ def load_table(index: DatasetIndex, row_start: int, row_stop: int,
                columns: Optional[Sequence[str]] = None,
                num_threads: int = 8,
                alloc: Optional[Callable[[Tuple[int, ...], np.dtype], np.ndarray]] = None,
-               on_read: Optional[Callable[[float, float], None]] = None) -> HostTable:
+               on_read: Optional[Callable[[float, float], None]] = None,
+               copy_fn: Optional[Callable[[np.ndarray, np.ndarray], None]] = None) -> HostTable:
     """Decode global rows ``[row_start, row_stop)``.
 
     ``alloc(shape, dtype)`` supplies the destination buffers (pinned host
     memory from the native runtime in GPU mode); default is plain numpy.
     ``on_read(total_duration, read_duration)`` is invoked per row group (feeds
-    the map-stage stats, the analogue of reference ``shuffle.py:147-167``)."""
+    the map-stage stats, the analogue of reference ``shuffle.py:147-167``).
+    ``copy_fn(dst, src)`` copies a decoded contiguous column slice into its
+    (pinned) destination - the native runtime's GIL-free parallel memcpy."""
     names = list(columns) if columns is not None else list(index.schema.keys())
     for n in names:
         if n not in index.schema:
@@ -173,7 +176,11 @@ def load_table(index: DatasetIndex, row_start: int, row_stop: int,
                 width = arr.shape[1]
                 schema[n] = (code, width)
             buf = _ensure(n, width, arr.dtype)
-            buf[dst:dst + (hi - lo)] = arr[lo:hi]
+            part = arr[lo:hi]
+            if copy_fn is not None and part.flags.c_contiguous and part.nbytes >= (1 << 20):
+                copy_fn(buf[dst:dst + (hi - lo)], part)
+            else:
+                buf[dst:dst + (hi - lo)] = part
         t2 = timeit.default_timer()
         return t2 - t0, t1 - t0
 

@@ -158,16 +158,19 @@ def test_generic_casts_match_golden(small_dataset):
 
 
 def test_one_d_bulk_path_matches_golden(tmp_path_factory):
-    """use_tensor_map=False: the cp.async.bulk (UBLKCP) path for arbitrary
-    column pointers must agree with the tensor-map (UTMALDG) path."""
+    """The three source-load paths - 1-D bulk copies (UBLKCP, default), swizzled
+    tensor-map boxes and one dense tensor-map box (UTMALDG) - must all agree
+    with the golden."""
     files = _float_files(tmp_path_factory, 70, name="o")
     cols = [f"f{i}" for i in range(69)] + ["labels"]
-    cpu, dev = _engines(files, _f32_layout(cols), 2, use_tensor_map=False)
-    assert dev.fast_mode == 0
-    try:
-        _compare_epochs(cpu, dev, epochs=(0, 1))
-    finally:
-        dev.close(); cpu.close()
+    for mode in (0, 1, 2):
+        cpu, dev = _engines(files, _f32_layout(cols), 2)
+        dev.tmap_mode = mode
+        assert dev.fast_mode == 0
+        try:
+            _compare_epochs(cpu, dev, epochs=(0, 1))
+        finally:
+            dev.close(); cpu.close()
 
 
 def test_forced_generic_equals_fast(tmp_path_factory):

@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--verify", action="store_true")
     ap.add_argument("--no-tmap", action="store_true", help="use 1-D bulk copies")
+    ap.add_argument("--tmap-mode", type=int, default=0, help="1: swizzled 32-row boxes, 2: dense box")
     ap.add_argument("--ext", default=None, help="path to an alternative _C build")
     ap.add_argument("--tag", default="")
     a = ap.parse_args()
@@ -86,9 +87,10 @@ def main():
                             scale_offset=scale_off, dst=dst_ptrs, mode=a.mode,
                             grid=min(a.grid or sm * _C.fast_ctas_per_sm(a.mode), tiles),
                             stream=stream,
-                            col_base=0 if a.no_tmap else src.data_ptr(),
-                            col_stride=0 if a.no_tmap else rows_pad * 4,
-                            rows_alloc=0 if a.no_tmap else rows_pad)
+                            col_base=0 if (a.no_tmap or not a.tmap_mode) else src.data_ptr(),
+                            col_stride=0 if (a.no_tmap or not a.tmap_mode) else rows_pad * 4,
+                            rows_alloc=0 if (a.no_tmap or not a.tmap_mode) else rows_pad,
+                            tmap_mode=a.tmap_mode)
     for i in range(a.warmup):
         launch(i)
     torch.cuda.synchronize()
@@ -118,7 +120,7 @@ def main():
             os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    out = {"tag": a.tag, "tmap": not a.no_tmap, "tile_rows": _C.fast_tile_rows(a.mode) if a.mode < 3 else 0,
+    out = {"tag": a.tag, "tmap": (0 if a.no_tmap else a.tmap_mode), "tile_rows": _C.fast_tile_rows(a.mode) if a.mode < 3 else 0,
            "rows": n, "cols": F, "mode": a.mode, "trainers": T, "row_pitch": pitch,
            "ms_best": best, "ms_median": med, "gbps_best": bytes_moved / best / 1e6,
            "gbps_median": bytes_moved / med / 1e6, "bytes": bytes_moved, "grid": a.grid or sm}
