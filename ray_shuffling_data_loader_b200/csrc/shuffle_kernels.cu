@@ -686,7 +686,9 @@ void launch_scatter_generic(GenericParams p, int grid, cudaStream_t stream) {
   if (p.n_local == 0) return;
   const size_t budget = 160 * 1024;
   uint32_t rows = static_cast<uint32_t>(budget / (p.row_pitch + 4 + sizeof(unsigned long long)));
-  rows = rows >= 256 ? 256 : (rows / 32) * 32;
+  // 128 rows per block keeps the staging tile small enough for several CTAs per
+  // SM: the per-thread field loop is latency bound, occupancy hides it.
+  rows = rows >= 128 ? 128 : (rows / 32) * 32;
   if (rows == 0) throw std::runtime_error("row pitch too large for the generic scatter kernel");
   p.rows_per_block = rows;
   const size_t smem = static_cast<size_t>(rows) * (p.row_pitch + 4 + sizeof(unsigned long long)) + 16;
@@ -697,6 +699,14 @@ void launch_scatter_generic(GenericParams p, int grid, cudaStream_t stream) {
                                          static_cast<int>(budget + 4096));
     if (e != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     configured = budget + 4096;
+  }
+  if (grid <= 0) {
+    int per_sm = static_cast<int>(std::min<size_t>(8, (200 * 1024) / (smem + 1024)));
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned long long blocks = (p.n_local + rows - 1) / rows;
+    grid = static_cast<int>(std::min<unsigned long long>(blocks, static_cast<unsigned long long>(sms) * std::max(1, per_sm)));
   }
   scatter_generic_kernel<<<grid, 256, smem, stream>>>(p);
   cudaError_t e = cudaGetLastError();

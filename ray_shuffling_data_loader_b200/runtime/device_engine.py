@@ -437,7 +437,7 @@ class DeviceShuffleEngine:
                               num_fields=len(self.generic_field_idx), n_local=n_rows,
                               global_offset=global_offset, row_pitch=lay.row_pitch,
                               write_lo=lo, write_hi=hi, dst=dst,
-                              grid=max(1, min(self.sm_count * 2, -(-n_rows // 64))),
+                              grid=self.grid_override or 0,   # 0: launcher picks by occupancy
                               stream=self.shuffle_stream)
             self.launches += 1
 

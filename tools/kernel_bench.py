@@ -79,7 +79,7 @@ def main():
             _C.scatter_generic(key=key, num_rows=n, num_trainers=T, fields=fields.data_ptr(),
                                num_fields=F, n_local=n, global_offset=0, row_pitch=pitch,
                                write_lo=0, write_hi=pitch, dst=dst_ptrs,
-                               grid=a.grid or sm * 2, stream=stream)
+                               grid=a.grid, stream=stream)
         else:
             tiles = -(-n // _C.fast_tile_rows(a.mode))
             _C.scatter_fast(key=key, num_rows=n, num_trainers=T, cols=ptrs.data_ptr(),
