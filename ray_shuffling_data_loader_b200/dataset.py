@@ -159,7 +159,7 @@ class ShufflingDataset:
             device = None      # decided by the first chunk that arrives
         if output is None and device is not None:
             output = "pandas" if device == "cpu" else "device"
-        if output not in (None, "pandas", "device", "packed"):
+        if output not in (None, "pandas", "device", "packed", "span"):
             raise ValueError(f"unknown output {output!r}")
         self._output = output
 
@@ -216,6 +216,10 @@ class ShufflingDataset:
         self._skip_batches = int(state.get("batches_consumed", 0))
 
     def _convert(self, packed, layout):
+        if self._output == "span":
+            return packed           # BatchSpan, or a materialised straddling batch
+        if isinstance(packed, BatchSpan):
+            packed = packed.packed()
         if self._output is None:
             import numpy as np
             self._output = "pandas" if isinstance(packed, np.ndarray) else "device"
@@ -359,6 +363,22 @@ class ShufflingDataset:
             pass
 
 
+class BatchSpan:
+    """Rows ``[start, stop)`` of one epoch buffer: a batch before any view is
+    built. ``output="span"`` yields these so wrappers can slice cached typed
+    views of the whole buffer instead of re-deriving them per batch."""
+    __slots__ = ("buffer", "start", "stop")
+
+    def __init__(self, buffer, start, stop):
+        self.buffer, self.start, self.stop = buffer, start, stop
+
+    def __len__(self):
+        return self.stop - self.start
+
+    def packed(self):
+        return self.buffer.view(self.start, self.stop)
+
+
 class _Rebatcher:
     """Carve exact ``batch_size`` batches out of successive chunks.
 
@@ -382,11 +402,13 @@ class _Rebatcher:
         self.rows += len(chunk)
 
     def _take(self, n: int):
+        """-> ``BatchSpan`` (rows of one epoch buffer, the zero-copy common case)
+        or a materialised array when the batch straddles different buffers."""
         pieces = []
         while n > 0:
             buf, start, stop = self.spans[0]
             k = min(n, stop - start)
-            pieces.append(buf.view(start, start + k))
+            pieces.append(BatchSpan(buf, start, start + k))
             if start + k == stop:
                 self.spans.pop(0)
             else:
@@ -395,11 +417,12 @@ class _Rebatcher:
             self.rows -= k
         if len(pieces) == 1:
             return pieces[0]
+        mats = [p.packed() for p in pieces]
         import numpy as np
-        if isinstance(pieces[0], np.ndarray):
-            return np.concatenate(pieces, axis=0)
+        if isinstance(mats[0], np.ndarray):
+            return np.concatenate(mats, axis=0)
         import torch
-        return torch.cat(pieces, dim=0)
+        return torch.cat(mats, dim=0)
 
     def pop_full(self):
         while self.rows >= self.batch_size:

@@ -102,10 +102,11 @@ class TorchShufflingDataset(IterableDataset):
             drop_last=drop_last,
             num_reducers=num_reducers,
             max_concurrent_epochs=max_concurrent_epochs,
-            output="packed",
+            output="span",
             layout_fn=self._layout_fn,
             **dataset_options)
         self._transform: Optional[Callable] = None
+        self._layout = None
 
     @property
     def dataset(self) -> ShufflingDataset:
@@ -137,18 +138,45 @@ class TorchShufflingDataset(IterableDataset):
         return self._transform
 
     def __iter__(self):
-        layout = None
-        for packed in iter(self._ds):
-            if layout is None:
+        from ray_shuffling_data_loader_b200.dataset import BatchSpan
+        cache = {}      # id(epoch buffer) -> (features, label) views of the WHOLE buffer
+        for item in iter(self._ds):
+            if isinstance(item, BatchSpan) and hasattr(item.buffer.data, "_offset"):
+                item = item.packed()      # chunk shipped from another process
+            if isinstance(item, BatchSpan):
+                buf = item.buffer
+                views = cache.get(id(buf))
+                if views is None:
+                    if len(cache) > 8:
+                        cache.clear()
+                    whole = buf.view(0, buf.rows)
+                    if isinstance(whole, np.ndarray):
+                        whole = torch.from_numpy(whole)
+                    self._layout = buf.layout
+                    views = cache[id(buf)] = (buf, packed_to_tensors(
+                        whole, buf.layout, self._spec, self._packed_features))
+                feats, label = views[1]
+                a, b = item.start, item.stop
+                # per batch: one row-slice per tensor of views built once per epoch
+                if isinstance(feats, list):
+                    f = [t[a:b] for t in feats]
+                elif isinstance(feats, tuple):
+                    f = tuple(t[a:b] for t in feats)
+                else:
+                    f = feats[a:b]
+                yield f, (label[a:b] if label is not None else None)
+                continue
+            packed = item           # a batch that straddled two buffers (copy)
+            if self._layout is None:
                 eng = self._ds.engine
                 if eng is None:
                     raise RuntimeError(
                         "TorchShufflingDataset needs the layout of the owning "
                         "process; construct it with rank 0 or in distributed mode")
-                layout = eng.layout
+                self._layout = eng.layout
             if isinstance(packed, np.ndarray):
                 packed = torch.from_numpy(packed)
-            yield packed_to_tensors(packed, layout, self._spec,
+            yield packed_to_tensors(packed, self._layout, self._spec,
                                     self._packed_features)
 
 
