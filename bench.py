@@ -60,6 +60,7 @@ def parse_args():
                                                          os.path.join(tempfile.gettempdir(), "rsdl_bench")))
     p.add_argument("--exchange", choices=["p2p", "nccl"], default="p2p")
     p.add_argument("--feature-dtype", choices=["float32", "bfloat16", "fp8"], default="float32")
+    p.add_argument("--peer-alloc", choices=["symm", "ipc"], default=None)
     p.add_argument("--skip-e2e", action="store_true")
     p.add_argument("--keep-data", action="store_true")
     p.add_argument("--ref-steps-cap", type=int, default=None,
@@ -227,6 +228,8 @@ def make_dataset(args, files, rank, world, epochs, resident, torch, seed=2026092
     dt = {"float32": torch.float32, "bfloat16": torch.bfloat16,
           "fp8": getattr(torch, "float8_e4m3fn", None)}[args.feature_dtype]
     opts = dict(resident=resident, exchange=args.exchange)
+    if args.peer_alloc:
+        opts["peer_alloc"] = args.peer_alloc
     if resident == "host":
         opts["stream_chunk_rows"] = args.batch_size
     fp8 = args.feature_dtype == "fp8"
@@ -239,6 +242,8 @@ def make_dataset(args, files, rank, world, epochs, resident, torch, seed=2026092
 
 
 def run_ours(args):
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
     import torch
     import torch.distributed as dist
     from ray_shuffling_data_loader_b200.parallel import bootstrap

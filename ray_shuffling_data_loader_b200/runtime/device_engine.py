@@ -105,7 +105,7 @@ class DeviceShuffleEngine:
                  flag_timeout_s: float = 300.0, index=None,
                  device_index: Optional[int] = None, grid: Optional[int] = None,
                  process_group=None, force_generic: bool = False,
-                 use_tensor_map: bool = True):
+                 use_tensor_map: bool = True, peer_alloc: Optional[str] = None):
         import torch
         self.C = load_native()
         self.torch = torch
@@ -139,6 +139,9 @@ class DeviceShuffleEngine:
         self.flag_timeout_s = flag_timeout_s
         self.force_generic = force_generic
         self.use_tensor_map = use_tensor_map
+        self.peer_alloc = peer_alloc or os.environ.get("RSDL_PEER_ALLOC", "symm")
+        if self.peer_alloc not in ("symm", "ipc"):
+            raise ValueError("peer_alloc must be 'symm' or 'ipc'")
         # Source tile loads: 0 = 1-D bulk copies (cp.async.bulk, fastest measured:
         # 512-byte contiguous DRAM reads), 1 = tensor-map boxes with 128B swizzle,
         # 2 = one dense tensor-map box per tile. See profiles/README.md.
@@ -188,13 +191,26 @@ class DeviceShuffleEngine:
         self.off_error = self.off_consumed + _align(T * 4, 128)
         self.header_bytes = _align(self.off_error + 16, 4096)
         self.arena_bytes = self.header_bytes + self.window * nloc * self.slot_bytes
+        self._symm = None
+        self._opened: List[int] = []
+        if self.world > 1 and self.peer_alloc == "symm":
+            # VMM-backed symmetric allocation (cuMemCreate + fd exchange, 2 MB
+            # pages, explicit peer access): measured 30x faster for the random row
+            # scatter than a legacy cudaIpc mapping of a cudaMalloc arena (see
+            # profiles/README.md, "NVLink").
+            try:
+                self._alloc_symmetric()
+                return
+            except Exception as e:  # pragma: no cover - depends on the driver stack
+                import warnings
+                warnings.warn(f"symmetric-memory arena unavailable ({e}); "
+                              "falling back to legacy CUDA IPC")
         self.arena = C.device_malloc(self.arena_bytes)
         # Zero once: flags start at 0 and row padding stays deterministic.
         C.device_memset_async(self.arena, 0, self.arena_bytes, self.shuffle_stream)
         C.stream_synchronize(self.shuffle_stream)
         # peer mapping (CUDA IPC) - rank r's arena base as seen from this process
         self.peer_base: List[int] = [self.arena] * self.world
-        self._opened: List[int] = []
         if self.world > 1:
             handle = C.ipc_get_handle(self.arena)
             handles = bootstrap.all_gather_object(
@@ -208,6 +224,23 @@ class DeviceShuffleEngine:
                 self._opened.append(base)
                 self.peer_base[r] = base
             bootstrap.barrier(self.pg)
+
+    def _alloc_symmetric(self):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        torch = self.torch
+        group = self.pg if self.pg is not None else dist.group.WORLD
+        t = symm_mem.empty((self.arena_bytes,), dtype=torch.uint8,
+                           device=torch.device("cuda", self.device_index))
+        hdl = symm_mem.rendezvous(t, group)
+        t.zero_()
+        torch.cuda.synchronize(self.device_index)
+        hdl.barrier()
+        self._symm = (t, hdl)
+        self.arena = t.data_ptr()
+        self.peer_base = [int(p) for p in hdl.buffer_ptrs]
+        if self.peer_base[self.rank] != self.arena:
+            self.peer_base[self.rank] = self.arena
 
     def _owner(self, trainer: int) -> Tuple[int, int]:
         """(owning rank, index among that rank's local trainers)."""
@@ -729,7 +762,9 @@ class DeviceShuffleEngine:
             C.pinned_free(self._desc_host_ptr)
             C.device_free(self.desc_arena)
             C.device_free(self.src_arena)
-            C.device_free(self.arena)
+            if self._symm is None:
+                C.device_free(self.arena)
+            self._symm = None
             C.stream_destroy(self.shuffle_stream)
             C.stream_destroy(self.copy_stream)
 

@@ -19,7 +19,8 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, files, ncols, dst_code, fp8, exchange, resident, out_dir):
+def _worker(rank, world, port, files, ncols, dst_code, fp8, exchange, resident, out_dir,
+            peer_alloc="symm"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
                       WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     import torch
@@ -37,7 +38,7 @@ def _worker(rank, world, port, files, ncols, dst_code, fp8, exchange, resident, 
                               fp8_block_scale=fp8)
     plan_args = dict(num_trainers=world, num_reducers=world, batch_size=1000, drop_last=False)
     gold = CpuShuffleEngine(files, plan_args, fn, 42)          # all trainers, one process
-    opts = dict(exchange=exchange, resident=resident)
+    opts = dict(exchange=exchange, resident=resident, peer_alloc=peer_alloc)
     if resident == "host":
         opts["stream_chunk_rows"] = 4096
     dev = DeviceShuffleEngine(files, plan_args, fn, 42, rank=rank, world=world, **opts)
@@ -68,14 +69,16 @@ def _files(tmp_path_factory, ncols, nrows=60_013):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("exchange,resident,dst,fp8", [
-    ("p2p", "hbm", 7, False), ("p2p", "host", 7, False), ("p2p", "hbm", 6, False),
-    ("p2p", "hbm", 9, True), ("nccl", "hbm", 7, False)])
-def test_multi_gpu_matches_golden(tmp_path_factory, tmp_path, exchange, resident, dst, fp8):
+@pytest.mark.parametrize("exchange,resident,dst,fp8,peer_alloc", [
+    ("p2p", "hbm", 7, False, "symm"), ("p2p", "host", 7, False, "symm"),
+    ("p2p", "hbm", 6, False, "symm"), ("p2p", "hbm", 9, True, "symm"),
+    ("p2p", "hbm", 7, False, "ipc"), ("nccl", "hbm", 7, False, "symm")])
+def test_multi_gpu_matches_golden(tmp_path_factory, tmp_path, exchange, resident, dst, fp8,
+                                  peer_alloc):
     import torch.multiprocessing as mp
     world = min(torch.cuda.device_count(), 8)
     files = _files(tmp_path_factory, 64)
     mp.spawn(_worker, args=(world, _free_port(), files, 64, dst, fp8, exchange, resident,
-                            str(tmp_path)), nprocs=world, join=True)
+                            str(tmp_path), peer_alloc), nprocs=world, join=True)
     for r in range(world):
         assert open(tmp_path / f"ok_{r}").read() == "1", f"rank {r} mismatch"

@@ -44,6 +44,11 @@ def main():
     ap.add_argument("--verify", action="store_true")
     ap.add_argument("--no-tmap", action="store_true", help="use 1-D bulk copies")
     ap.add_argument("--tmap-mode", type=int, default=0, help="1: swizzled 32-row boxes, 2: dense box")
+    ap.add_argument("--peer", type=int, default=-1,
+                    help="place the destination on this other GPU (single-process P2P)")
+    ap.add_argument("--peer-frac", type=float, default=1.0,
+                    help="with --peer and --trainers 2: trainer 0 local, trainer 1 on the peer")
+    ap.add_argument("--identity", action="store_true", help="identity permutation (sequential dst)")
     ap.add_argument("--ext", default=None, help="path to an alternative _C build")
     ap.add_argument("--tag", default="")
     a = ap.parse_args()
@@ -63,6 +68,14 @@ def main():
     dst = torch.zeros((T, per, pitch), dtype=torch.uint8, device="cuda")
     ptrs = torch.tensor([src[c].data_ptr() for c in range(F)], dtype=torch.int64, device="cuda")
     dst_ptrs = [dst[t].data_ptr() for t in range(T)]
+    if a.peer >= 0:
+        # single-process P2P: trainers >= 1 (or all, with one trainer) live on the peer GPU
+        _C.enable_peer_access(a.peer)
+        dst_peer = torch.zeros((T, per, pitch), dtype=torch.uint8, device=f"cuda:{a.peer}")
+        torch.cuda.synchronize(a.peer)
+        for t in range(T):
+            if T == 1 or t >= 1:
+                dst_ptrs[t] = dst_peer[t].data_ptr()
     stream = torch.cuda.current_stream().cuda_stream
     fields = None
     if a.mode == 3:
@@ -75,6 +88,8 @@ def main():
 
     def launch(epoch):
         key = list(perm.make_key(n, 1234, epoch).as_words())
+        if a.identity:
+            key = [1, 1, 1, 0, 0, 0, 0, 0, 0]
         if a.mode == 3:
             _C.scatter_generic(key=key, num_rows=n, num_trainers=T, fields=fields.data_ptr(),
                                num_fields=F, n_local=n, global_offset=0, row_pitch=pitch,
@@ -102,7 +117,7 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         times.append(e0.elapsed_time(e1))
-    if a.verify and a.mode in (0, 3):
+    if a.verify and a.mode in (0, 3) and a.peer < 0 and not a.identity:
         launch(7)
         torch.cuda.synchronize()
         pos = perm.permute(np.arange(min(n, 100000), dtype=np.uint64), perm.make_key(n, 1234, 7))
@@ -120,7 +135,7 @@ def main():
             os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    out = {"tag": a.tag, "tmap": (0 if a.no_tmap else a.tmap_mode), "tile_rows": _C.fast_tile_rows(a.mode) if a.mode < 3 else 0,
+    out = {"tag": a.tag, "peer": a.peer, "identity": a.identity, "tmap": (0 if a.no_tmap else a.tmap_mode), "tile_rows": _C.fast_tile_rows(a.mode) if a.mode < 3 else 0,
            "rows": n, "cols": F, "mode": a.mode, "trainers": T, "row_pitch": pitch,
            "ms_best": best, "ms_median": med, "gbps_best": bytes_moved / best / 1e6,
            "gbps_median": bytes_moved / med / 1e6, "bytes": bytes_moved, "grid": a.grid or sm}
