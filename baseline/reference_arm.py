@@ -26,11 +26,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def _unavailable(why: str):
-    print(json.dumps({"impl": "reference", "unavailable": why}), flush=True)
+    import bench
+    bench.emit_json({"impl": "reference", "unavailable": why})
     sys.exit(0)
 
 
 def main(args):
+    import bench
+    bench.claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
@@ -58,7 +61,6 @@ def main(args):
         sys.exit(0)
 
     # Input files: identical bytes for both arms (generated outside timing).
-    import bench
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
@@ -100,40 +102,52 @@ def main(args):
     dev = torch.device("cuda", torch.cuda.current_device())
     acc = torch.zeros(1, dtype=torch.float64, device=dev)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    done, total, epoch = 0, warmup + steps, 0
-    h2d_bytes = 0
-    wall0 = None
-    checksum = 0.0
-    finished = False
-    while not finished:
-        ds.set_epoch(epoch)
-        for data, target in ds:
-            if done == warmup:
-                torch.cuda.synchronize()
-                if world > 1:
-                    dist.barrier()
-                if sampler:
-                    sampler.start()
-                wall0 = time.perf_counter()
-                ev0.record()
-                h2d_bytes = 0
-            # the reference example's H2D: pageable .cuda() of every tensor
-            data = [t.cuda() for t in data]
-            target = target.cuda()
-            h2d_bytes += sum(t.numel() * t.element_size() for t in data) + \
-                target.numel() * target.element_size()
-            # same sink as our arm: reduce every value of the batch, read it back
-            acc += torch.stack([t.sum(dtype=torch.float64) for t in data]).sum() \
-                + target.sum(dtype=torch.float64)
-            checksum = float(acc.item())
-            done += 1
-            if done == total:
-                ev1.record()
-                torch.cuda.synchronize()
-                wall = time.perf_counter() - wall0
-                finished = True
-                break
-        epoch += 1
+    h2d = [0]
+    checksum = [0.0]
+    state = {"it": None, "epoch": 0}
+
+    def next_batch():
+        while True:
+            if state["it"] is None:
+                ds.set_epoch(state["epoch"])
+                state["it"] = iter(ds)
+            try:
+                return next(state["it"])
+            except StopIteration:
+                state["it"] = None
+                state["epoch"] += 1
+
+    def step():
+        data, target = next_batch()
+        # the reference example's H2D: pageable .cuda() of every tensor
+        data = [t.cuda() for t in data]
+        target = target.cuda()
+        h2d[0] += sum(t.numel() * t.element_size() for t in data) + \
+            target.numel() * target.element_size()
+        # same sink as our arm: reduce every value of the batch, read it back
+        nonlocal_acc = torch.stack([t.sum(dtype=torch.float64) for t in data]).sum() \
+            + target.sum(dtype=torch.float64)
+        acc.add_(nonlocal_acc)
+        checksum[0] = float(acc.item())
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    if sampler:
+        sampler.start()
+    h2d[0] = 0
+    # like our arm: the clock starts BEFORE the first timed batch is fetched
+    wall0 = time.perf_counter()
+    ev0.record()
+    for _ in range(steps):
+        step()
+    ev1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - wall0
+    h2d_bytes = h2d[0]
+    checksum = checksum[0]
     clocks = sampler.stop() if sampler else None
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
     wall_t = torch.tensor([wall], dtype=torch.float64, device=dev)
@@ -165,7 +179,7 @@ def main(args):
             "note": "reference has no device-resident mode: value == e2e "
                     "(host shuffle + pageable H2D every step)",
         }
-        print(json.dumps(out), flush=True)
+        bench.emit_json(out)
     # leave quickly: the reference's shuffle driver may still be producing epochs
     if world > 1:
         dist.barrier()

@@ -44,6 +44,28 @@ ROW_GROUPS_PER_FILE = 5
 METRIC = "rows_per_sec"
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout: move the real stdout aside and
+    point fd 1 at stderr so that library chatter (e.g. NCCL's version banner,
+    printed with printf) cannot interleave with it."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+        sys.stdout = sys.stderr
+    return _JSON_OUT
+
+
+def emit_json(obj):
+    out = claim_stdout()
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
@@ -168,57 +190,67 @@ class ClockSampler:
 # ---------------------------------------------------------------------------
 
 def run_phase(ds, engine, torch, dist, world, steps, warmup, batch_size, d2h_each_step):
+    """Consume ``warmup`` then ``steps`` batches. The clock starts BEFORE the first
+    timed batch is fetched, so waiting for that batch's epoch to be shuffled is
+    inside the timed region (no pre-shuffled epoch is consumed for free).
+    Returns (max-over-ranks device ms, wall s, launches in the region, checksum)."""
     row_pitch = engine.layout.row_pitch
-    """Consume warmup + steps batches; returns (max-over-ranks device ms, wall s,
-    launches in the timed region, checksum)."""
     dev = torch.device("cuda", torch.cuda.current_device())
     acc = torch.zeros(1, dtype=torch.float64, device=dev)
     host_acc = torch.zeros(1, dtype=torch.float64).pin_memory()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    done = 0
-    total = warmup + steps
-    epoch = 0
-    launches0 = wall0 = None
-    checksum = 0.0
-    while done < total:
-        ds.set_epoch(epoch)
-        for features, label in ds:      # the public API: (features[B, F-1], label[B, 1])
-            if done == warmup:
-                torch.cuda.synchronize()
-                if world > 1:
-                    dist.barrier()
-                torch.cuda.synchronize()
-                launches0 = engine.launches
-                wall0 = time.perf_counter()
-                ev0.record()
-            # consume: every byte of the batch (features + label share one packed
-            # row; the feature view starts at the batch's first byte) is read by
-            # our reduction kernel
-            base = features[0] if isinstance(features, tuple) else features
-            engine.batch_sum_all(base, acc, nbytes=base.shape[0] * row_pitch)
-            if d2h_each_step:
-                host_acc.copy_(acc, non_blocking=True)
-                torch.cuda.current_stream().synchronize()
-                checksum = float(host_acc[0])
-            done += 1
-            if done == total:
-                ev1.record()
-                torch.cuda.synchronize()
-                wall = time.perf_counter() - wall0
-                if world > 1:
-                    dist.barrier()
-                torch.cuda.synchronize()
-                launches = engine.launches - launches0
-                break
-        epoch += 1
+    state = {"it": None, "epoch": 0}
+
+    def next_batch():
+        while True:
+            if state["it"] is None:
+                ds.set_epoch(state["epoch"])
+                state["it"] = iter(ds)
+            try:
+                return next(state["it"])       # the public API: (features, label)
+            except StopIteration:
+                state["it"] = None
+                state["epoch"] += 1
+
+    checksum = [0.0]
+
+    def step():
+        features, label = next_batch()
+        # consume: every byte of the batch (features + label share one packed row;
+        # the feature view starts at the batch's first byte) is read by our kernel
+        base = features[0] if isinstance(features, tuple) else features
+        engine.batch_sum_all(base, acc, nbytes=base.shape[0] * row_pitch)
+        if d2h_each_step:
+            host_acc.copy_(acc, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            checksum[0] = float(host_acc[0])
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = engine.launches
+    wall0 = time.perf_counter()
+    ev0.record()
+    for _ in range(steps):
+        step()
+    ev1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - wall0
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches = engine.launches - launches0
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
     wall_t = torch.tensor([wall], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(wall_t, op=dist.ReduceOp.MAX)
     if not d2h_each_step:
-        checksum = float(acc.item())
-    return float(ms.item()), float(wall_t.item()), launches, checksum
+        checksum[0] = float(acc.item())
+    return float(ms.item()), float(wall_t.item()), launches, checksum[0]
 
 
 def make_dataset(args, files, rank, world, epochs, resident, torch, seed=20260921):
@@ -242,8 +274,7 @@ def make_dataset(args, files, rank, world, epochs, resident, torch, seed=2026092
 
 
 def run_ours(args):
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
-        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
+    claim_stdout()
     import torch
     import torch.distributed as dist
     from ray_shuffling_data_loader_b200.parallel import bootstrap
@@ -332,7 +363,7 @@ def run_ours(args):
             "ingest_seconds": ingest_s, "datagen_seconds": gen_s, "fast_mode": fast_mode,
             "checksum": chk,
         }
-        print(json.dumps(out), flush=True)
+        emit_json(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
