@@ -30,6 +30,7 @@ using rsdl::FastParams;
 using rsdl::FieldDev;
 using rsdl::FlagTargets;
 using rsdl::GenericParams;
+using rsdl::WideParams;
 
 namespace {
 
@@ -400,6 +401,29 @@ PYBIND11_MODULE(_C, m) {
         py::arg("key"), py::arg("num_rows"), py::arg("num_trainers"), py::arg("fields"),
         py::arg("num_fields"), py::arg("n_local"), py::arg("global_offset"),
         py::arg("row_pitch"), py::arg("write_lo"), py::arg("write_hi"), py::arg("dst"),
+        py::arg("grid"), py::arg("stream"));
+  m.def("scatter_wide",
+        [](const std::vector<uint64_t>& key, uint64_t num_rows, uint32_t num_trainers,
+           uintptr_t src, uint32_t width, uint32_t src_code, uint32_t dst_code, uint32_t dst_off,
+           uint64_t n_local, uint64_t global_offset, uint32_t row_pitch,
+           const std::vector<uintptr_t>& dst, int grid, uintptr_t stream) {
+          WideParams p;
+          p.key = make_key(key);
+          p.plan = make_plan(num_rows, num_trainers);
+          p.src = as_ptr<const uint8_t>(src);
+          p.width = width;
+          p.src_code = src_code;
+          p.dst_code = dst_code;
+          p.dst_off = dst_off;
+          p.n_local = n_local;
+          p.global_offset = global_offset;
+          p.row_pitch = row_pitch;
+          fill_dst(p, dst);
+          rsdl::launch_scatter_wide(p, grid, as_stream(stream));
+        },
+        py::arg("key"), py::arg("num_rows"), py::arg("num_trainers"), py::arg("src"),
+        py::arg("width"), py::arg("src_code"), py::arg("dst_code"), py::arg("dst_off"),
+        py::arg("n_local"), py::arg("global_offset"), py::arg("row_pitch"), py::arg("dst"),
         py::arg("grid"), py::arg("stream"));
   m.attr("FIELD_DESC_BYTES") = sizeof(FieldDev);
   m.def("perm_positions",

@@ -48,6 +48,21 @@ struct GenericParams {
   uint8_t* dst[RSDL_MAX_TRAINERS];
 };
 
+// Wide path: one list-valued column ([n, width] row-major) -> one field per row.
+struct WideParams {
+  PermKeyDev key;
+  PlanDev plan;
+  const uint8_t* src;
+  uint32_t width;
+  uint32_t src_code;
+  uint32_t dst_code;
+  uint32_t dst_off;
+  unsigned long long n_local;
+  unsigned long long global_offset;
+  uint32_t row_pitch;
+  uint8_t* dst[RSDL_MAX_TRAINERS];
+};
+
 struct FlagTargets {
   uint32_t* ptr[RSDL_MAX_TRAINERS];
   uint32_t count;
@@ -60,6 +75,7 @@ int fast_max_tile_rows();
 
 void launch_scatter_fast(const FastParams& p, int mode, int grid, cudaStream_t stream);
 void launch_scatter_generic(GenericParams p, int grid, cudaStream_t stream);
+void launch_scatter_wide(const WideParams& p, int grid, cudaStream_t stream);
 void launch_perm_positions(const PermKeyDev& key, const PlanDev& plan,
                            unsigned long long global_offset, unsigned long long n_local,
                            int32_t* trainer, long long* slot, cudaStream_t stream);

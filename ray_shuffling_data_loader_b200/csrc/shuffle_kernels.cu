@@ -528,6 +528,61 @@ __global__ void __launch_bounds__(256) scatter_generic_kernel(const GenericParam
 }
 
 // ---------------------------------------------------------------------------
+// K2 wide path: list-valued columns ([N, width] row-major, e.g. images)
+// ---------------------------------------------------------------------------
+// The source is already row-major, so the scatter is a permuted row copy with an
+// optional cast: one warp per row, 16-byte vector loads and stores on both sides.
+__global__ void __launch_bounds__(256) scatter_wide_kernel(const WideParams p) {
+  const int lane = threadIdx.x & 31;
+  const unsigned long long warp0 =
+      (blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x) >> 5;
+  const unsigned long long nwarps = (static_cast<unsigned long long>(gridDim.x) * blockDim.x) >> 5;
+  const uint32_t ss = rsdl_itemsize(p.src_code), ds = rsdl_itemsize(p.dst_code);
+  const unsigned long long src_row_bytes = static_cast<unsigned long long>(p.width) * ss;
+  const bool vec_copy = (p.src_code == p.dst_code) && (src_row_bytes % 16 == 0) &&
+                        (p.dst_off % 16 == 0) && (p.row_pitch % 16 == 0) &&
+                        ((reinterpret_cast<unsigned long long>(p.src) & 15) == 0);
+  const bool vec_bf16 = (p.src_code == DT_F32 && p.dst_code == DT_BF16) && (p.width % 8 == 0) &&
+                        (p.dst_off % 16 == 0) && (p.row_pitch % 16 == 0) &&
+                        ((reinterpret_cast<unsigned long long>(p.src) & 15) == 0);
+  for (unsigned long long r = warp0; r < p.n_local; r += nwarps) {
+    const unsigned long long d =
+        dest_pointer(p.global_offset + r, p.key, p.plan, p.dst, p.row_pitch) + p.dst_off;
+    const uint8_t* src = p.src + r * src_row_bytes;
+    if (vec_copy) {
+      const uint4* s4 = reinterpret_cast<const uint4*>(src);
+      uint4* d4 = reinterpret_cast<uint4*>(d);
+      const uint32_t nvec = static_cast<uint32_t>(src_row_bytes / 16);
+      for (uint32_t v = lane; v < nvec; v += 32) d4[v] = __ldg(s4 + v);
+    } else if (vec_bf16) {
+      const float4* s4 = reinterpret_cast<const float4*>(src);
+      uint4* d4 = reinterpret_cast<uint4*>(d);
+      const uint32_t nvec = p.width / 8;
+      for (uint32_t v = lane; v < nvec; v += 32) {
+        const float4 a = __ldg(s4 + 2 * v), b = __ldg(s4 + 2 * v + 1);
+        uint4 o;
+        o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w);
+        o.z = pack_bf16x2(b.x, b.y); o.w = pack_bf16x2(b.z, b.w);
+        d4[v] = o;
+      }
+    } else {
+      for (uint32_t e = lane; e < p.width; e += 32) {
+        bool is_int, from_f64; long long iv; double fv; float sv;
+        load_src(src + static_cast<unsigned long long>(e) * ss, p.src_code, &is_int, &iv, &fv, &sv, &from_f64);
+        uint8_t* out = reinterpret_cast<uint8_t*>(d) + static_cast<unsigned long long>(e) * ds;
+        if (ds == 8) {
+          // store_cast writes 8-byte values as two words (alignment-agnostic)
+          store_cast(out, p.dst_code, is_int, iv, fv, sv, from_f64);
+        } else {
+          store_cast(out, p.dst_code, is_int, iv, fv, sv, from_f64);
+        }
+      }
+    }
+  }
+  __threadfence_system();
+}
+
+// ---------------------------------------------------------------------------
 // K1 standalone: positions of local rows (tests, NCCL baseline)
 // ---------------------------------------------------------------------------
 __global__ void perm_positions_kernel(PermKeyDev key, PlanDev plan, unsigned long long global_offset,
@@ -711,6 +766,20 @@ void launch_scatter_generic(GenericParams p, int grid, cudaStream_t stream) {
   scatter_generic_kernel<<<grid, 256, smem, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("scatter_generic launch: ") + cudaGetErrorString(e));
+}
+
+void launch_scatter_wide(const WideParams& p, int grid, cudaStream_t stream) {
+  if (p.n_local == 0) return;
+  if (grid <= 0) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned long long blocks = (p.n_local + 7) / 8;
+    grid = static_cast<int>(std::min<unsigned long long>(blocks, static_cast<unsigned long long>(sms) * 8));
+  }
+  scatter_wide_kernel<<<grid, 256, 0, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string("scatter_wide launch: ") + cudaGetErrorString(e));
 }
 
 static void check_launch(const char* what) {

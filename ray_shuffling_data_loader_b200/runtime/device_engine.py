@@ -283,12 +283,16 @@ class DeviceShuffleEngine:
         for b in range(self.num_src_bufs):
             ptrs = self.src_col_ptrs[b]
             fast_cols = np.array([ptrs[i] for i in self.fast_field_idx], dtype=np.uint64)
-            gen = np.zeros(len(self.generic_field_idx), dtype=_FIELD_DTYPE)
-            for k, i in enumerate(self.generic_field_idx):
-                f = self.src_fields[i]
-                gen[k] = (ptrs[i], f.src_code, f.dst_code, f.offset, f.width)
-            tables.append((fast_cols, gen))
-        blob = b"".join(_pad(a.tobytes()) + _pad(g.tobytes()) for a, g in tables)
+            runs = []
+            for idxs, _lo, _hi in self.generic_runs:
+                gen = np.zeros(len(idxs), dtype=_FIELD_DTYPE)
+                for k, i in enumerate(idxs):
+                    f = self.src_fields[i]
+                    gen[k] = (ptrs[i], f.src_code, f.dst_code, f.offset, f.width)
+                runs.append(gen)
+            tables.append((fast_cols, runs))
+        blob = b"".join(_pad(a.tobytes()) + b"".join(_pad(g.tobytes()) for g in runs)
+                        for a, runs in tables)
         self.desc_arena = C.device_malloc(max(256, len(blob)))
         self._desc_host, self._desc_host_ptr = pinned_array(C, (max(256, len(blob)),), np.uint8)
         self._desc_host[:len(blob)] = np.frombuffer(blob, dtype=np.uint8)
@@ -296,32 +300,76 @@ class DeviceShuffleEngine:
         C.stream_synchronize(self.shuffle_stream)
         self.fast_cols_dev, self.generic_fields_dev = [], []
         off = self.desc_arena
-        for a, g in tables:
+        for a, runs in tables:
             self.fast_cols_dev.append(off)
             off += len(_pad(a.tobytes()))
-            self.generic_fields_dev.append(off)
-            off += len(_pad(g.tobytes()))
+            run_ptrs = []
+            for g in runs:
+                run_ptrs.append(off)
+                off += len(_pad(g.tobytes()))
+            self.generic_fields_dev.append(run_ptrs)
         if self.resident == "host":
             self.h2d_done = [C.event_create(False) for _ in range(self.num_src_bufs)]
             self.buf_free = [C.event_create(False) for _ in range(self.num_src_bufs)]
             self._buf_used = [False] * self.num_src_bufs
 
+    _WIDE_MIN = 16      # list columns at least this wide use the row-major copy kernel
+
     def _plan_kernels(self):
-        """Split the layout's fields between the TMA fast kernel and the generic
-        kernel (see csrc/shuffle_kernels.cu)."""
+        """Split the layout's fields between the three scatter kernels
+        (csrc/shuffle_kernels.cu): the TMA fast kernel (a dense prefix of 4-byte
+        scalar columns), the wide kernel (list-valued columns, already row-major)
+        and the generic kernel (everything else, one launch per contiguous run of
+        its fields so launches never write each other's bytes)."""
         lay = self.layout
         fields = self.src_fields
         self.fast_mode = -1
         self.fast_field_idx: List[int] = []
-        self.generic_field_idx = list(range(len(fields)))
-        self.generic_range = (0, lay.row_pitch)
-        if self.force_generic or not fields:
-            return
-        # longest prefix that is dense from 0, width 1, one 4-byte source dtype,
-        # one destination dtype that the fast kernel can emit
+        self.wide_field_idx: List[int] = []
+        nfast, fast_ranges = 0, []
+        if not self.force_generic and fields:
+            nfast, fast_ranges, mode = self._fast_prefix()
+            if nfast:
+                self.fast_mode = mode
+                self.fast_field_idx = list(range(nfast))
+        rest = list(range(nfast, len(fields)))
+        if not self.force_generic:
+            self.wide_field_idx = [i for i in rest if fields[i].width >= self._WIDE_MIN]
+        generic = [i for i in rest if i not in self.wide_field_idx]
+        # contiguous runs of generic fields (by offset) between fast / wide ranges
+        taken = list(fast_ranges) if nfast else []
+        taken += [(fields[i].offset, fields[i].offset + fields[i].dst_bytes)
+                  for i in self.wide_field_idx]
+        generic.sort(key=lambda i: fields[i].offset)
+        runs: List[Tuple[List[int], int, int]] = []
+        for i in generic:
+            lo = fields[i].offset // 4 * 4
+            hi = _align(fields[i].offset + fields[i].dst_bytes, 4)
+            if runs:
+                idxs, rlo, rhi = runs[-1]
+                blocked = any(a < hi and b > rhi for a, b in taken)   # something in between
+                if not blocked:
+                    runs[-1] = (idxs + [i], rlo, max(rhi, hi))
+                    continue
+            runs.append(([i], lo, hi))
+        if not nfast and not self.wide_field_idx and runs:
+            # pure generic layout: one launch owns the whole row (padding included)
+            runs = [(sum((r[0] for r in runs), []), 0, lay.row_pitch)]
+        for idxs, lo, hi in runs:
+            for a, b in taken:
+                if a < hi and b > lo:
+                    raise ValueError("packed-row fields overlap between kernels; "
+                                     "reorder feature columns so same-typed scalars are adjacent")
+        self.generic_runs = runs
+        self.generic_field_idx = [i for r in runs for i in r[0]]
+
+    def _fast_prefix(self):
+        """(number of leading fields the TMA kernel takes, byte ranges it writes,
+        mode) - (0, [], -1) when the layout does not start with such a prefix."""
+        lay, fields = self.layout, self.src_fields
         first = fields[0]
         if first.width != 1 or L.itemsize(first.src_code) != 4 or first.offset != 0:
-            return
+            return 0, [], -1
         if first.dst_code == first.src_code:
             mode = 0
         elif first.src_code == L.DT_F32 and first.dst_code == L.DT_BF16:
@@ -330,7 +378,7 @@ class DeviceShuffleEngine:
               and lay.scale_offset >= 0):
             mode = 2
         else:
-            return
+            return 0, [], -1
         n, off = 0, 0
         dsz = L.itemsize(first.dst_code)
         for f in fields:
@@ -339,22 +387,20 @@ class DeviceShuffleEngine:
                 break
             n += 1
             off += dsz
-        rest = list(range(n, len(fields)))
-        if rest:
-            # The fast kernel writes whole 16-byte groups (and, in fp8 mode, the
-            # scale bytes); the remainder must start past them.
-            fast_end = _align(off, 16)
-            rest_lo = min(fields[i].offset for i in rest) // 4 * 4
-            scale_lo = lay.scale_offset if mode == 2 else lay.row_pitch
-            rest_hi = _align(max(fields[i].offset + fields[i].dst_bytes for i in rest), 4)
-            if rest_lo < fast_end or (mode == 2 and rest_hi > scale_lo):
-                return
-            self.generic_range = (rest_lo, rest_hi)
         if n < 4:
-            return      # not worth a TMA launch
-        self.fast_mode = mode
-        self.fast_field_idx = list(range(n))
-        self.generic_field_idx = rest
+            return 0, [], -1       # not worth a TMA launch
+        fast_end = _align(off, 16)  # the kernel writes whole 16-byte groups
+        rest = fields[n:]
+        if rest:
+            rest_lo = min(f.offset for f in rest)
+            rest_hi = max(f.offset + f.dst_bytes for f in rest)
+            scale_lo = lay.scale_offset if mode == 2 else lay.row_pitch
+            if rest_lo < fast_end or (mode == 2 and rest_hi > scale_lo):
+                return 0, [], -1
+        ranges = [(0, fast_end)]
+        if mode == 2:               # plus the UE8M0 scale bytes after everything else
+            ranges.append((lay.scale_offset, lay.scale_offset + (n + 31) // 32))
+        return n, ranges, mode
 
     # ------------------------------------------------------------------
     # ingest
@@ -462,12 +508,19 @@ class DeviceShuffleEngine:
                            rows_alloc=(stride // 4) if uniform else 0,
                            tmap_mode=self.tmap_mode)
             self.launches += 1
-        if self.generic_field_idx:
-            lo, hi = self.generic_range
+        for i in self.wide_field_idx:
+            f = self.src_fields[i]
+            C.scatter_wide(key=key_words, num_rows=plan.num_rows,
+                           num_trainers=plan.num_trainers, src=self.src_col_ptrs[buf][i],
+                           width=f.width, src_code=f.src_code, dst_code=f.dst_code,
+                           dst_off=f.offset, n_local=n_rows, global_offset=global_offset,
+                           row_pitch=lay.row_pitch, dst=dst, grid=self.grid_override or 0,
+                           stream=self.shuffle_stream)
+            self.launches += 1
+        for (idxs, lo, hi), fields_dev in zip(self.generic_runs, self.generic_fields_dev[buf]):
             C.scatter_generic(key=key_words, num_rows=plan.num_rows,
-                              num_trainers=plan.num_trainers,
-                              fields=self.generic_fields_dev[buf],
-                              num_fields=len(self.generic_field_idx), n_local=n_rows,
+                              num_trainers=plan.num_trainers, fields=fields_dev,
+                              num_fields=len(idxs), n_local=n_rows,
                               global_offset=global_offset, row_pitch=lay.row_pitch,
                               write_lo=lo, write_hi=hi, dst=dst,
                               grid=self.grid_override or 0,   # 0: launcher picks by occupancy

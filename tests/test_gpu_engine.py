@@ -214,3 +214,53 @@ def test_stream_wait_mode(tmp_path_factory):
         dev.check_error()
     finally:
         dev.close(); cpu.close()
+
+
+def _image_files(tmp_path_factory, n=3001, px=3 * 16 * 16):
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    d = tmp_path_factory.mktemp("img")
+    rng = np.random.default_rng(0)
+    files = []
+    for i, (a, b) in enumerate([(0, n // 3), (n // 3, n)]):
+        img = rng.random((b - a, px), dtype=np.float32)
+        tbl = pa.table({"image": pa.FixedSizeListArray.from_arrays(pa.array(img.reshape(-1)), px),
+                        "labels": pa.array(np.arange(a, b, dtype=np.int64)),
+                        "w": pa.array(rng.random(b - a).astype(np.float32))})
+        fn = str(d / f"img{i}.parquet")
+        pq.write_table(tbl, fn, row_group_size=500)
+        files.append(fn)
+    return files, px
+
+
+@pytest.mark.parametrize("dst", [L.DT_F32, L.DT_BF16, L.DT_F16])
+def test_wide_list_column_matches_golden(tmp_path_factory, dst):
+    """List-valued (image) columns take the row-major wide kernel; the int64
+    label and a float scalar ride the generic kernel next to it."""
+    files, px = _image_files(tmp_path_factory)
+
+    def fn(schema):
+        return L.build_layout([("image", L.DT_F32, dst, px), ("labels", L.DT_I64, L.DT_I64, 1),
+                               ("w", L.DT_F32, L.DT_F32, 1)])
+    cpu, dev = _engines(files, fn, 2)
+    assert dev.wide_field_idx == [0] and dev.fast_mode == -1 and len(dev.generic_runs) == 1
+    try:
+        _compare_epochs(cpu, dev, epochs=(0, 1))
+    finally:
+        dev.close(); cpu.close()
+
+
+def test_wide_column_streaming_and_torch_api(tmp_path_factory):
+    files, px = _image_files(tmp_path_factory)
+    from ray_shuffling_data_loader_b200 import TorchShufflingDataset
+    ds = TorchShufflingDataset(files, 2, 1, 256, 0, num_reducers=2, feature_columns=["image"],
+                               feature_shapes=[(3, 16, 16)], feature_types=[torch.bfloat16],
+                               label_column="labels", label_type=torch.int64, seed=1,
+                               queue_name="gw", resident="host", stream_chunk_rows=512)
+    for epoch in range(2):
+        ds.set_epoch(epoch)
+        labels = []
+        for (img,), y in ds:
+            assert img.is_cuda and img.dtype == torch.bfloat16 and img.shape[1:] == (3, 16, 16)
+            labels.append(y[:, 0].clone())
+        assert sorted(torch.cat(labels).tolist()) == list(range(3001))
