@@ -483,7 +483,10 @@ __device__ __forceinline__ void load_src(const uint8_t* src, uint32_t code, bool
 __global__ void __launch_bounds__(256) scatter_generic_kernel(const GenericParams p) {
   extern __shared__ __align__(16) uint8_t gsm[];
   const uint32_t R = p.rows_per_block;
-  const uint32_t spitch = p.row_pitch + 4;     // odd word count: conflict-free columns
+  // Only the byte range this launch owns is staged (a 8-byte label next to a
+  // 24 KB image row must not cost 24 KB of shared memory per row).
+  const uint32_t span = p.write_hi - p.write_lo;
+  const uint32_t spitch = span + 4;            // odd word count: conflict-free columns
   unsigned long long* dptr = reinterpret_cast<unsigned long long*>(gsm);
   uint8_t* stage = gsm + R * sizeof(unsigned long long);
   const int lane = threadIdx.x & 31;
@@ -507,7 +510,7 @@ __global__ void __launch_bounds__(256) scatter_generic_kernel(const GenericParam
       const FieldDev f = p.fields[fi];
       const uint32_t ss = rsdl_itemsize(f.src_code), ds = rsdl_itemsize(f.dst_code);
       const uint8_t* src = f.src + (row0 + r) * static_cast<unsigned long long>(ss) * f.width;
-      uint8_t* out = stage + r * spitch + f.dst_off;
+      uint8_t* out = stage + r * spitch + (f.dst_off - p.write_lo);
       for (uint32_t w = 0; w < f.width; ++w) {
         bool is_int, from_f64; long long iv; double fv; float sv;
         load_src(src + w * ss, f.src_code, &is_int, &iv, &fv, &sv, &from_f64);
@@ -516,11 +519,11 @@ __global__ void __launch_bounds__(256) scatter_generic_kernel(const GenericParam
     }
     __syncthreads();
     // phase 2: one warp per row, 128 B contiguous per store instruction
-    const uint32_t w_lo = p.write_lo / 4, w_hi = p.write_hi / 4;
+    const uint32_t nwords = span / 4;
     for (uint32_t r = warp; r < rows; r += nwarps) {
-      uint32_t* drow = reinterpret_cast<uint32_t*>(dptr[r]);
+      uint32_t* drow = reinterpret_cast<uint32_t*>(dptr[r] + p.write_lo);
       const uint32_t* srow = reinterpret_cast<const uint32_t*>(stage + r * spitch);
-      for (uint32_t w = w_lo + lane; w < w_hi; w += 32) drow[w] = srow[w];
+      for (uint32_t w = lane; w < nwords; w += 32) drow[w] = srow[w];
     }
     __syncthreads();
   }
@@ -740,13 +743,16 @@ void launch_scatter_fast(const FastParams& p, int mode, int grid, cudaStream_t s
 void launch_scatter_generic(GenericParams p, int grid, cudaStream_t stream) {
   if (p.n_local == 0) return;
   const size_t budget = 160 * 1024;
-  uint32_t rows = static_cast<uint32_t>(budget / (p.row_pitch + 4 + sizeof(unsigned long long)));
+  if (p.write_hi <= p.write_lo || p.write_hi > p.row_pitch || (p.write_lo & 3) || (p.write_hi & 3))
+    throw std::runtime_error("scatter_generic: bad write range");
+  const uint32_t span = p.write_hi - p.write_lo;
+  uint32_t rows = static_cast<uint32_t>(budget / (span + 4 + sizeof(unsigned long long)));
   // 128 rows per block keeps the staging tile small enough for several CTAs per
   // SM: the per-thread field loop is latency bound, occupancy hides it.
   rows = rows >= 128 ? 128 : (rows / 32) * 32;
   if (rows == 0) throw std::runtime_error("row pitch too large for the generic scatter kernel");
   p.rows_per_block = rows;
-  const size_t smem = static_cast<size_t>(rows) * (p.row_pitch + 4 + sizeof(unsigned long long)) + 16;
+  const size_t smem = static_cast<size_t>(rows) * (span + 4 + sizeof(unsigned long long)) + 16;
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(scatter_generic_kernel,
