@@ -347,13 +347,13 @@ PYBIND11_MODULE(_C, m) {
            uintptr_t cols, uint32_t num_cols, uint64_t n_local, uint64_t global_offset,
            uint32_t row_pitch, uint32_t scale_offset, const std::vector<uintptr_t>& dst, int mode,
            int grid, uintptr_t stream, uintptr_t col_base, uint64_t col_stride,
-           uint64_t rows_alloc, int tmap_mode) {
+           uint64_t rows_alloc, int tmap_mode, uintptr_t kinds, uint32_t write_end, int sched) {
           FastParams p;
           std::memset(&p.tmap, 0, sizeof(p.tmap));
           p.use_tmap = 0;
           const uint32_t tile_rows = static_cast<uint32_t>(rsdl::fast_tile_rows(mode));
           if (tmap_mode != 0 && col_base != 0 && col_stride % 16 == 0 &&
-              rows_alloc % tile_rows == 0) {
+              rows_alloc % tile_rows == 0 && rsdl::fast_src_itemsize(mode) == 4) {
             const bool dense = tmap_mode == 2;
             make_source_tmap(&p.tmap, col_base, rows_alloc, num_cols, col_stride,
                              static_cast<uint32_t>(rsdl::fast_panel_cols(mode)),
@@ -363,6 +363,7 @@ PYBIND11_MODULE(_C, m) {
           p.key = make_key(key);
           p.plan = make_plan(num_rows, num_trainers);
           p.cols = as_ptr<const uint8_t* const>(cols);
+          p.kinds = as_ptr<const uint8_t>(kinds);
           p.num_cols = num_cols;
           const uint32_t panel = static_cast<uint32_t>(rsdl::fast_panel_cols(mode));
           p.num_panels = (num_cols + panel - 1) / panel;
@@ -370,6 +371,14 @@ PYBIND11_MODULE(_C, m) {
           p.global_offset = global_offset;
           p.row_pitch = row_pitch;
           p.scale_offset = scale_offset;
+          if (write_end > row_pitch || (write_end & 15u))
+            throw std::runtime_error("scatter_fast: write_end must be a 16-byte multiple <= row_pitch");
+          p.write_end = write_end;
+          // auto: the cooperative schedule only wins for ~256-byte f32 rows
+          // (profiles/kbench_v17.jsonl: 64 cols 1.09 vs 1.20 ms; 32/48/96/128+ cols
+          // equal or worse; bf16 and 8-byte sources worse)
+          p.sched = sched >= 0 ? static_cast<uint32_t>(sched)
+                               : ((mode == 0 && num_cols > 48 && num_cols <= 80) ? 1u : 0u);
           fill_dst(p, dst);
           rsdl::launch_scatter_fast(p, mode, grid, as_stream(stream));
         },
@@ -377,7 +386,9 @@ PYBIND11_MODULE(_C, m) {
         py::arg("num_cols"), py::arg("n_local"), py::arg("global_offset"), py::arg("row_pitch"),
         py::arg("scale_offset"), py::arg("dst"), py::arg("mode"), py::arg("grid"),
         py::arg("stream"), py::arg("col_base") = 0, py::arg("col_stride") = 0,
-        py::arg("rows_alloc") = 0, py::arg("tmap_mode") = 2);
+        py::arg("rows_alloc") = 0, py::arg("tmap_mode") = 2, py::arg("kinds") = 0,
+        py::arg("write_end") = 0, py::arg("sched") = -1);
+  m.def("fast_src_itemsize", &rsdl::fast_src_itemsize);
   m.def("fast_ctas_per_sm", &rsdl::fast_ctas_per_sm);
   m.def("scatter_generic",
         [](const std::vector<uint64_t>& key, uint64_t num_rows, uint32_t num_trainers,

@@ -10,19 +10,23 @@
 
 namespace rsdl {
 
-// Fast path: every source column is a 4-byte scalar (see shuffle_kernels.cu).
+// Fast path: every source column is a 4-byte (modes 0-2) or 8-byte (modes 3-4)
+// scalar (see shuffle_kernels.cu).
 struct FastParams {
   alignas(64) CUtensorMap tmap;      // [num_cols][rows] view of the source columns
   uint32_t use_tmap;                 // 0: 1-D bulk copies from `cols` pointers
   PermKeyDev key;
   PlanDev plan;
   const uint8_t* const* cols;        // device array [num_cols] of column bases
+  const uint8_t* kinds;              // mode 4: device array [num_cols] of conversion kinds
   uint32_t num_cols;
   uint32_t num_panels;               // ceil(num_cols / panel width)
   unsigned long long n_local;        // rows owned by this rank
   unsigned long long global_offset;  // global index of local row 0
   uint32_t row_pitch;                // destination row pitch (bytes)
   uint32_t scale_offset;             // fp8 mode: byte offset of the UE8M0 scales
+  uint32_t sched;                    // producer schedule: 0 loader warps, 1 cooperative
+  uint32_t write_end;                // bytes [num_cols*dsz, write_end) of a row are zero-filled
   uint8_t* dst[RSDL_MAX_TRAINERS];   // epoch-slot base per trainer (local/peer)
 };
 
@@ -71,6 +75,7 @@ struct FlagTargets {
 int fast_panel_cols(int mode);
 int fast_ctas_per_sm(int mode);
 int fast_tile_rows(int mode);
+int fast_src_itemsize(int mode);
 int fast_max_tile_rows();
 
 void launch_scatter_fast(const FastParams& p, int mode, int grid, cudaStream_t stream);

@@ -45,6 +45,26 @@
 #ifndef RSDL_CTAS_F32
 #define RSDL_CTAS_F32 1
 #endif
+#ifndef RSDL_PANEL_F32
+#define RSDL_PANEL_F32 64
+#endif
+// Consumer warp groups (8 warps each) that take alternate pipeline stages. One
+// group has 2 warps per SM sub-partition: enough for 64 x 4-byte columns (the
+// tile is 32 KB of work), but latency bound for narrow tables - DATA_SPEC's 21
+// columns leave each consumer warp one short dependent chain per tile
+// (profiles/scatter_typed64_v7_mode4_21cols.md: stall_wait + branch_resolving).
+#ifndef RSDL_CGROUPS_F32
+#define RSDL_CGROUPS_F32 1
+#endif
+#ifndef RSDL_CGROUPS_64
+#define RSDL_CGROUPS_64 1
+#endif
+#ifndef RSDL_TILE_64
+#define RSDL_TILE_64 128
+#endif
+#ifndef RSDL_STAGES_64
+#define RSDL_STAGES_64 4
+#endif
 
 namespace rsdl {
 
@@ -123,6 +143,12 @@ __device__ __forceinline__ void sts64(void* p, unsigned long long v) {
 
 // 16-byte store to a (possibly peer-mapped) global address.
 __device__ __forceinline__ void stg128(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+#ifdef RSDL_EXPERIMENT_NO_STORE
+  // experiment only (never in the shipped build): keep the value dependency,
+  // drop the store, to measure the pipeline without its DRAM writes
+  if (a == 0x7fc12345u && b == c) asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+  return;
+#endif
   asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c),
                "r"(d)
                : "memory");
@@ -170,11 +196,25 @@ template <int MODE> struct ModeTraits;
 // TILE rows per tile: 256 makes every 1-D bulk copy 1 KB (the TMA unit retires
 // roughly one op per ~46 cycles per SM, so 512-byte copies cap the read rate near
 // 3 TB/s); INDEX_WARPS x 32 threads each own TILE/(32*INDEX_WARPS) rows' pointers.
-template <> struct ModeTraits<0> { static constexpr int FPL = 4;  static constexpr int PANEL = 64;  static constexpr int TILE = RSDL_TILE_F32; static constexpr int STAGES = RSDL_STAGES_F32; static constexpr int MIN_CTAS = RSDL_CTAS_F32; };
-template <> struct ModeTraits<1> { static constexpr int FPL = 8;  static constexpr int PANEL = 64;  static constexpr int TILE = RSDL_TILE_F32; static constexpr int STAGES = RSDL_STAGES_F32; static constexpr int MIN_CTAS = RSDL_CTAS_F32; };
-template <> struct ModeTraits<2> { static constexpr int FPL = 16; static constexpr int PANEL = 128; static constexpr int TILE = 128; static constexpr int STAGES = 3; static constexpr int MIN_CTAS = 1; };
-constexpr int kIndexWarps = 4;
-constexpr int kThreads = 32 * (1 + kIndexWarps + kConsumerWarps);
+// SRC = source itemsize in bytes. Modes 3/4 take 8-byte source columns (int64 /
+// float64: the reference's DATA_SPEC schema, data_generation.py:56-77) - mode 3
+// copies them bit for bit (plain ShufflingDataset rows), mode 4 converts every
+// column to a 4-byte destination (the default torch.float feature/label types,
+// torch_dataset.py:181-198) with a per-column conversion kind.
+template <> struct ModeTraits<0> { static constexpr int CGROUPS = RSDL_CGROUPS_F32; static constexpr int SRC = 4; static constexpr int FPL = 4;  static constexpr int PANEL = RSDL_PANEL_F32;  static constexpr int TILE = RSDL_TILE_F32; static constexpr int STAGES = RSDL_STAGES_F32; static constexpr int MIN_CTAS = RSDL_CTAS_F32; };
+template <> struct ModeTraits<1> { static constexpr int CGROUPS = RSDL_CGROUPS_F32; static constexpr int SRC = 4; static constexpr int FPL = 8;  static constexpr int PANEL = 64;  static constexpr int TILE = RSDL_TILE_F32; static constexpr int STAGES = RSDL_STAGES_F32; static constexpr int MIN_CTAS = RSDL_CTAS_F32; };
+template <> struct ModeTraits<2> { static constexpr int CGROUPS = 1; static constexpr int SRC = 4; static constexpr int FPL = 16; static constexpr int PANEL = 128; static constexpr int TILE = 128; static constexpr int STAGES = 3; static constexpr int MIN_CTAS = 1; };
+template <> struct ModeTraits<3> { static constexpr int CGROUPS = RSDL_CGROUPS_64; static constexpr int SRC = 8; static constexpr int FPL = 2;  static constexpr int PANEL = 32;  static constexpr int TILE = RSDL_TILE_64; static constexpr int STAGES = RSDL_STAGES_64; static constexpr int MIN_CTAS = 1; };
+template <> struct ModeTraits<4> { static constexpr int CGROUPS = RSDL_CGROUPS_64; static constexpr int SRC = 8; static constexpr int FPL = 4;  static constexpr int PANEL = 32;  static constexpr int TILE = RSDL_TILE_64; static constexpr int STAGES = RSDL_STAGES_64; static constexpr int MIN_CTAS = 1; };
+// Warp roles: [0, kLoaderWarps) issue the TMA loads, the next kIndexWarps
+// evaluate the permutation, the rest transpose + cast + scatter.
+#ifndef RSDL_INDEX_WARPS
+#define RSDL_INDEX_WARPS 4
+#endif
+constexpr int kLoaderWarps = 4;
+constexpr int kIndexWarps = RSDL_INDEX_WARPS;
+template <int MODE> constexpr int kThreadsFor =
+    32 * (kLoaderWarps + kIndexWarps + kConsumerWarps * ModeTraits<MODE>::CGROUPS);
 
 // Two shared-memory tile layouts (both conflict-free for the consumers):
 //  * tensor-map path: kTileRows/32 TMA boxes of [PANEL cols][32 rows] with the
@@ -188,59 +228,73 @@ struct alignas(1024) FastSmem {
   static constexpr int PANEL = ModeTraits<MODE>::PANEL;
   static constexpr int STAGES = ModeTraits<MODE>::STAGES;
   static constexpr int TILE = ModeTraits<MODE>::TILE;
-  static constexpr int kPitchWords = TILE + 4;   // 1-D path: words per column
+  static constexpr int kPitchWords = TILE * (ModeTraits<MODE>::SRC / 4) + 4;   // 1-D path: words per column
   static constexpr int kTileWords = ((PANEL * kPitchWords + 255) / 256) * 256;
   float tile[STAGES][kTileWords];
   unsigned long long dptr[STAGES][TILE];
   uint64_t full[STAGES];       // TMA bytes landed
   uint64_t idx_full[STAGES];   // destination pointers written
   uint64_t empty[STAGES];      // consumers done with the stage
+  uint64_t turn[kIndexWarps];  // token ring: index warps publish tiles in order
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, ModeTraits<MODE>::MIN_CTAS)
+__global__ void __launch_bounds__(kThreadsFor<MODE>, ModeTraits<MODE>::MIN_CTAS)
 scatter_tma_kernel(const __grid_constant__ FastParams p) {
   using T = ModeTraits<MODE>;
   constexpr int FPL = T::FPL;
   constexpr int PANEL = T::PANEL;
   constexpr int STAGES = T::STAGES;
   constexpr int kTileRows = T::TILE;
-  constexpr int kPitchWords = kTileRows + 4;
+  constexpr int SRC = T::SRC;
+  constexpr int kPitchWords = kTileRows * (SRC / 4) + 4;
   constexpr int kBoxesPerTile = kTileRows / kBoxRows;
-  constexpr int kRowsPerIndexThread = kTileRows / (32 * kIndexWarps);
   constexpr int PASSES = PANEL / (8 * FPL);
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment: the 128-byte TMA swizzle is a function of address bits
   const uint32_t raw = smem_u32(smem_raw);
   FastSmem<MODE>& sm = *reinterpret_cast<FastSmem<MODE>*>(smem_raw + ((1024u - (raw & 1023u)) & 1023u));
-  const bool tmap = p.use_tmap != 0;      // 1: 32-row boxes, 128B swizzle; 2: one dense box
-  const bool dense = p.use_tmap == 2;
+  // 1: 32-row boxes, 128B swizzle; 2: one dense box (4-byte sources only)
+  const bool tmap = SRC == 4 && p.use_tmap != 0;
+  const bool dense = SRC == 4 && p.use_tmap == 2;
+  // Producer schedule (FastParams::sched):
+  //  0  dedicated loader warps issue a stage's loads the moment it is released;
+  //     every index warp owns whole tiles (kTileRows/32 rows per lane) - best for
+  //     narrow tables, bf16 / 8-byte modes (index bound otherwise);
+  //  1  "cooperative": the index warps share every tile (one row per lane) and
+  //     issue the tile's loads themselves after publishing its index; measured
+  //     10% faster for 64 x f32 (1.08 vs 1.20 ms, profiles/kbench_v16.jsonl) where
+  //     the paced load issue interleaves better with the consumers' row writes.
+  static_assert(kLoaderWarps == kIndexWarps, "full[] arrival count is shared by both schedules");
+  const bool coop = p.sched == 1 && !tmap;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&sm.full[s], tmap ? 1 : kIndexWarps);
-      mbar_init(&sm.idx_full[s], kIndexWarps);
+      mbar_init(&sm.full[s], tmap ? 1 : kLoaderWarps);   // expect_tx arrivals (== kIndexWarps)
+      mbar_init(&sm.idx_full[s], coop ? kIndexWarps : 1);   // index warp(s) of the tile
       mbar_init(&sm.empty[s], kConsumerWarps);
     }
+    for (int w = 0; w < kIndexWarps; ++w) mbar_init(&sm.turn[w], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
   const unsigned long long num_tiles = (p.n_local + kTileRows - 1) / kTileRows;
 
-  if (warp == 0) {
-    // ===== producer (tensor-map path): kBoxesPerTile TMA box loads per tile =====
-    if (tmap && lane == 0) {
+  if (warp < kLoaderWarps) {
+    if (tmap) {
+    // ===== loader (tensor-map path): kBoxesPerTile TMA box loads per tile =====
+    if (warp == 0 && lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap) : "memory");
       int stage = 0;
       uint32_t phase = 0;
       for (unsigned long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
       for (uint32_t panel = 0; panel < p.num_panels; ++panel) {
         mbar_wait(&sm.empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&sm.full[stage], PANEL * kTileRows * 4u);
+        mbar_arrive_expect_tx(&sm.full[stage], PANEL * kTileRows * 4u);   // SRC == 4 here
         if (dense) {
           // one [PANEL cols][TILE rows] box: 512-byte (or 1 KB) contiguous DRAM
           // reads per column, un-swizzled smem (2-way LDS conflicts, cheap)
@@ -256,57 +310,178 @@ scatter_tma_kernel(const __grid_constant__ FastParams p) {
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp <= kIndexWarps) {
-    // ===== index warps: the tile's shared permutation index =====
-    // One Feistel evaluation per thread per tile, running STAGES tiles ahead of
-    // the consumers; column panels of the same rows reuse the previous result.
-    const int r = threadIdx.x - 32;            // first row owned inside the tile
-    int stage = 0;
-    uint32_t phase = 0;
-    for (unsigned long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      // evaluated once per (row, tile); every column panel of the tile reuses it
-      unsigned long long prev[kRowsPerIndexThread];
-#pragma unroll
-      for (int i = 0; i < kRowsPerIndexThread; ++i) {
-        const unsigned long long lr = tile * kTileRows + r + i * (32 * kIndexWarps);
-        prev[i] = (lr < p.n_local)
-            ? dest_pointer(p.global_offset + lr, p.key, p.plan, p.dst, p.row_pitch)
-            : 0ull;
-      }
-      for (uint32_t panel = 0; panel < p.num_panels; ++panel) {
-      mbar_wait(&sm.empty[stage], phase ^ 1);
-#pragma unroll
-      for (int i = 0; i < kRowsPerIndexThread; ++i)
-        sts64(&sm.dptr[stage][r + i * (32 * kIndexWarps)], prev[i]);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.idx_full[stage]);
-      if (!tmap) {
-        // 1-D bulk path: each index warp loads its share of the panel's columns
-        // (issue is serialised per lane, so spread it over the warps).
-        const uint32_t col0 = panel * PANEL;
-        const uint32_t ncols = min(static_cast<uint32_t>(PANEL), p.num_cols - col0);
-        const uint32_t w = warp - 1;
-        const uint32_t per = (ncols + kIndexWarps - 1) / kIndexWarps;
-        const uint32_t c_lo = min(w * per, ncols), c_hi = min(c_lo + per, ncols);
-        if (lane == 0) mbar_arrive_expect_tx(&sm.full[stage], (c_hi - c_lo) * kTileRows * 4u);
-        __syncwarp();
-        for (uint32_t c = c_lo + lane; c < c_hi; c += 32) {
-          const uint8_t* src = p.cols[col0 + c] + tile * kTileRows * 4ull;
-          tma_load_1d(&sm.tile[stage][c * kPitchWords], src, kTileRows * 4u, &sm.full[stage]);
-        }
-      }
-      if (++stage == STAGES) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else {
-    // ===== consumers: transpose + cast + scatter =====
-    const int cwarp = warp - 1 - kIndexWarps;
-    const int rho = lane & 3;
-    const int q = lane >> 2;
+    } else if (!coop) {
+    // ===== loaders (1-D bulk path): one cp.async.bulk per column of the panel =====
+    // A warp issues its UBLKCPs one lane at a time (~65 cycles each) while the
+    // TMA unit retires one per ~46 cycles, so every panel's columns are split
+    // over the kLoaderWarps warps; all of them take part in every iteration, in
+    // order, which keeps the parity test on empty[] valid.
     int stage = 0;
     uint32_t phase = 0;
     for (unsigned long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
     for (uint32_t panel = 0; panel < p.num_panels; ++panel) {
+      const uint32_t col0 = panel * PANEL;
+      const uint32_t ncols = min(static_cast<uint32_t>(PANEL), p.num_cols - col0);
+      const uint32_t per = (ncols + kLoaderWarps - 1) / kLoaderWarps;
+      const uint32_t c_lo = min(warp * per, ncols), c_hi = min(c_lo + per, ncols);
+      mbar_wait(&sm.empty[stage], phase ^ 1);
+      if (lane == 0) mbar_arrive_expect_tx(&sm.full[stage], (c_hi - c_lo) * kTileRows * SRC);
+      __syncwarp();
+      for (uint32_t c = c_lo + lane; c < c_hi; c += 32) {
+        const uint8_t* src = p.cols[col0 + c] + tile * static_cast<unsigned long long>(kTileRows * SRC);
+        // 8-byte sources: odd column blocks sit 16 bytes later (fits exactly in
+        // the 16-byte column padding) so that a quarter-warp's two column
+        // blocks fall in different 16-byte bank groups - see the consumer.
+        const uint32_t shift = (SRC == 8) ? (((c / FPL) & 1u) << 2) : 0u;
+        tma_load_1d(&sm.tile[stage][c * kPitchWords + shift], src, kTileRows * SRC, &sm.full[stage]);
+      }
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+    }
+  } else if (warp < kLoaderWarps + kIndexWarps) {
+    // ===== index warps: the tile's shared permutation index =====
+    // Each index warp owns whole tiles (round-robin), so kIndexWarps tiles are
+    // indexed concurrently, and a lane evaluates the Feistel network for
+    // kTileRows/32 rows at once (independent dependency chains). With all index
+    // warps cooperating on one tile (one row per lane) the serial chain
+    // "cycle-walk (max over the lanes) -> publish -> issue loads" bounded the
+    // tile rate at ~1.2 us regardless of the row width, i.e. narrow tables ran at
+    // a third of the HBM rate (profiles/README.md, v8 -> v9).
+    //
+    // Publishing stays strictly in tile order through a token ring of mbarriers
+    // (turn[w] is completed by warp w-1 when it is done with its tile): the
+    // parity test on empty[] is only meaningful for a waiter that is at most one
+    // phase ahead of the barrier, which free-running warps would not guarantee.
+    // The expensive part - the Feistel evaluations - happens before the token
+    // is awaited.
+    const int w = warp - kLoaderWarps;
+    if (coop) {
+      // schedule 1: all index warps cooperate on every tile and load it
+      constexpr int kRows = kTileRows / (32 * kIndexWarps);
+      const int r = w * 32 + lane;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (unsigned long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        unsigned long long prev[kRows];
+#pragma unroll
+        for (int i = 0; i < kRows; ++i) {
+          const unsigned long long lr = tile * kTileRows + r + i * (32 * kIndexWarps);
+          prev[i] = (lr < p.n_local)
+              ? dest_pointer(p.global_offset + lr, p.key, p.plan, p.dst, p.row_pitch) : 0ull;
+        }
+        for (uint32_t panel = 0; panel < p.num_panels; ++panel) {
+          mbar_wait(&sm.empty[stage], phase ^ 1);
+#pragma unroll
+          for (int i = 0; i < kRows; ++i) sts64(&sm.dptr[stage][r + i * (32 * kIndexWarps)], prev[i]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm.idx_full[stage]);
+          {
+            const uint32_t col0 = panel * PANEL;
+            const uint32_t ncols = min(static_cast<uint32_t>(PANEL), p.num_cols - col0);
+            const uint32_t per = (ncols + kIndexWarps - 1) / kIndexWarps;
+            const uint32_t c_lo = min(w * per, ncols), c_hi = min(c_lo + per, ncols);
+            if (lane == 0) mbar_arrive_expect_tx(&sm.full[stage], (c_hi - c_lo) * kTileRows * SRC);
+            __syncwarp();
+            for (uint32_t c = c_lo + lane; c < c_hi; c += 32) {
+              const uint8_t* src = p.cols[col0 + c] + tile * static_cast<unsigned long long>(kTileRows * SRC);
+              const uint32_t shift = (SRC == 8) ? (((c / FPL) & 1u) << 2) : 0u;
+              tma_load_1d(&sm.tile[stage][c * kPitchWords + shift], src, kTileRows * SRC, &sm.full[stage]);
+            }
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else {
+    constexpr int RPL = kTileRows / 32;        // rows per lane
+    int stage = 0;
+    uint32_t phase = 0;
+    int owner = 0;
+    uint32_t round = 0;                        // tiles this warp has published
+    for (unsigned long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const bool mine = owner == w;
+      if (++owner == kIndexWarps) owner = 0;
+      if (!mine) {
+        for (uint32_t panel = 0; panel < p.num_panels; ++panel)
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        continue;
+      }
+      // evaluated once per (row, tile); every column panel of the tile reuses it
+      unsigned long long prev[RPL];
+      {
+        unsigned long long x[RPL];
+        bool valid[RPL];
+#pragma unroll
+        for (int i = 0; i < RPL; ++i) {
+          const unsigned long long lr = tile * kTileRows + lane + 32 * i;
+          valid[i] = lr < p.n_local;
+          x[i] = valid[i] ? p.global_offset + lr : 0ull;
+        }
+        if (p.key.n > 1) {
+#pragma unroll
+          for (int i = 0; i < RPL; ++i) x[i] = rsdl_feistel(x[i], p.key);
+          // Cycle-walk the rows that left [0, n) (same result as rsdl_permute).
+          // About a quarter of the rows need it and very few need it twice, so
+          // after the first (RPL-way interleaved) evaluation each round walks
+          // ONE row per lane - the lane's first row still outside - instead of
+          // re-evaluating all RPL: the kernel is issue bound for narrow tables
+          // (profiles/README.md, v11-v13), and the round count (max over the
+          // warp) stays about the same while a round costs 1/RPL of the work.
+          while (true) {
+            int sel = -1;
+#pragma unroll
+            for (int i = RPL - 1; i >= 0; --i) sel = (x[i] >= p.key.n) ? i : sel;
+            if (!__any_sync(0xffffffffu, sel >= 0)) break;
+            unsigned long long xs = x[0];
+#pragma unroll
+            for (int i = 1; i < RPL; ++i) xs = (sel == i) ? x[i] : xs;
+            const unsigned long long y = rsdl_feistel(xs, p.key);
+#pragma unroll
+            for (int i = 0; i < RPL; ++i) x[i] = (sel == i) ? y : x[i];
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < RPL; ++i) {
+          uint32_t trainer;
+          unsigned long long slot;
+          rsdl_position_to_dest(x[i], p.plan, &trainer, &slot);
+          prev[i] = valid[i]
+              ? reinterpret_cast<unsigned long long>(p.dst[trainer]) + slot * p.row_pitch
+              : 0ull;
+        }
+      }
+      // the token: warp 0 holds it initially (waits for the phase *before* its round)
+      mbar_wait(&sm.turn[w], (round & 1u) ^ (w == 0 ? 1u : 0u));
+      ++round;
+      for (uint32_t panel = 0; panel < p.num_panels; ++panel) {
+        mbar_wait(&sm.empty[stage], phase ^ 1);
+#pragma unroll
+        for (int i = 0; i < RPL; ++i) sts64(&sm.dptr[stage][lane + 32 * i], prev[i]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.idx_full[stage]);
+        if (lane == 0 && panel + 1 == p.num_panels) mbar_arrive(&sm.turn[(w + 1) % kIndexWarps]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+    }  // schedule 0
+  } else {
+    // ===== consumers: transpose + cast + scatter =====
+    const int cwarp = (warp - kLoaderWarps - kIndexWarps) % kConsumerWarps;
+    const int cgroup = (warp - kLoaderWarps - kIndexWarps) / kConsumerWarps;
+    const int rho = lane & 3;
+    const int q = lane >> 2;
+    int stage = 0;
+    uint32_t phase = 0;
+    int turn = 0;                              // which consumer group owns this iteration
+    for (unsigned long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+    for (uint32_t panel = 0; panel < p.num_panels; ++panel) {
+      if (T::CGROUPS > 1) {
+        const bool mine = turn == cgroup;
+        if (++turn == T::CGROUPS) turn = 0;
+        if (!mine) {
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          continue;
+        }
+      }
       const uint32_t col0 = panel * PANEL;
       const uint32_t ncols = min(static_cast<uint32_t>(PANEL), p.num_cols - col0);
       mbar_wait(&sm.idx_full[stage], phase);
@@ -317,11 +492,83 @@ scatter_tma_kernel(const __grid_constant__ FastParams p) {
         unsigned long long d[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) d[j] = lds64(&sm.dptr[stage][rg * 4 + j]);
+        if constexpr (SRC == 8) {
+          // 8-byte sources. Column c lives at word c*kPitchWords (+4 for odd column
+          // blocks); rows 4rg..4rg+3 of it are two 16-byte groups whose bank
+          // group is (c + [block odd] + 2rg + h) mod 8 - distinct for the 8 lanes
+          // {q0, q0+1} x {rho 0..3} of a quarter-warp.
+#pragma unroll
+          for (int pass = 0; pass < PASSES; ++pass) {
+            const int cb = q + 8 * pass;
+            const uint32_t f0 = cb * FPL;
+            // columns past the last one are written as zeros up to write_end (the
+            // row's padding), so that no 32-byte sector is left partially written
+            if (f0 >= ncols && (col0 + f0) * (16u / FPL) >= p.write_end) continue;
+            unsigned long long v[FPL][4];
+#pragma unroll
+            for (int k = 0; k < FPL; ++k) {
+              const uint32_t f = f0 + k;
+              if (f < ncols) {
+                const float* w = A + f * kPitchWords + ((cb & 1) << 2) + rg * 8;
+                const float4 lo = lds128(w), hi = lds128(w + 4);
+                v[k][0] = (static_cast<unsigned long long>(__float_as_uint(lo.y)) << 32) | __float_as_uint(lo.x);
+                v[k][1] = (static_cast<unsigned long long>(__float_as_uint(lo.w)) << 32) | __float_as_uint(lo.z);
+                v[k][2] = (static_cast<unsigned long long>(__float_as_uint(hi.y)) << 32) | __float_as_uint(hi.x);
+                v[k][3] = (static_cast<unsigned long long>(__float_as_uint(hi.w)) << 32) | __float_as_uint(hi.z);
+              } else {
+                v[k][0] = v[k][1] = v[k][2] = v[k][3] = 0ull;
+              }
+            }
+            if (MODE == 3) {
+              const uint32_t off = (col0 + f0) * 8u;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (d[j])
+                  stg128(reinterpret_cast<void*>(d[j] + off), static_cast<uint32_t>(v[0][j]),
+                         static_cast<uint32_t>(v[0][j] >> 32), static_cast<uint32_t>(v[1][j]),
+                         static_cast<uint32_t>(v[1][j] >> 32));
+              }
+            } else {
+              // kind 0: int64 -> f32 (RNE), 1: float64 -> f32 (RNE), 2: int64 -> int32.
+              // The table is padded to a multiple of 4 entries: one aligned word
+              // holds this lane's 4 kinds. All-int64->f32 (the common case) runs
+              // branch free; mixed blocks compute both conversions and select.
+              const uint32_t k4 = (f0 < ncols)
+                  ? __ldg(reinterpret_cast<const uint32_t*>(p.kinds + col0 + f0)) : 0u;
+              uint32_t o[FPL][4];
+              if (k4 == 0u) {
+#pragma unroll
+                for (int k = 0; k < FPL; ++k)
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    o[k][j] = __float_as_uint(__ll2float_rn(static_cast<long long>(v[k][j])));
+              } else {
+#pragma unroll
+                for (int k = 0; k < FPL; ++k) {
+                  const uint32_t kind = (k4 >> (8 * k)) & 0xFFu;
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const uint32_t fi = __float_as_uint(__ll2float_rn(static_cast<long long>(v[k][j])));
+                    const uint32_t fd = __float_as_uint(
+                        __double2float_rn(__longlong_as_double(static_cast<long long>(v[k][j]))));
+                    o[k][j] = kind == 0u ? fi : (kind == 1u ? fd : static_cast<uint32_t>(v[k][j]));
+                  }
+                }
+              }
+              const uint32_t off = (col0 + f0) * 4u;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (d[j]) stg128(reinterpret_cast<void*>(d[j] + off), o[0][j], o[1][j], o[2 % FPL][j], o[3 % FPL][j]);
+              }
+            }
+          }
+        } else {
 #pragma unroll
         for (int pass = 0; pass < PASSES; ++pass) {
           const int cb = q + 8 * pass;            // column block inside the panel
           const uint32_t f0 = cb * FPL;
-          const bool active = f0 < ncols;
+          // (columns past the last one: zeros up to write_end, see the 8-byte path)
+          const bool active = f0 < ncols || (MODE != 2 && (col0 + f0) * (16u / FPL) < p.write_end);
           // (fp8 mode exchanges amax with the partner lane: nobody may skip)
           if (MODE != 2 && !active) continue;
           float v[FPL][4];
@@ -396,6 +643,7 @@ scatter_tma_kernel(const __grid_constant__ FastParams p) {
             }
           }
         }
+        }  // SRC == 4
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.empty[stage]);
@@ -720,12 +968,22 @@ static void launch_fast_mode(const FastParams& p, int grid, cudaStream_t stream)
     if (e != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     configured = true;
   }
-  scatter_tma_kernel<MODE><<<grid, kThreads, smem, stream>>>(p);
+  scatter_tma_kernel<MODE><<<grid, kThreadsFor<MODE>, smem, stream>>>(p);
 }
 
-int fast_panel_cols(int mode) { return mode == 2 ? ModeTraits<2>::PANEL : ModeTraits<0>::PANEL; }
-int fast_ctas_per_sm(int mode) { return mode == 2 ? ModeTraits<2>::MIN_CTAS : ModeTraits<0>::MIN_CTAS; }
-int fast_tile_rows(int mode) { return mode == 2 ? ModeTraits<2>::TILE : ModeTraits<0>::TILE; }
+#define RSDL_MODE_SWITCH(mode, EXPR)                     \
+  switch (mode) {                                        \
+    case 0: { using M = ModeTraits<0>; return EXPR; }    \
+    case 1: { using M = ModeTraits<1>; return EXPR; }    \
+    case 2: { using M = ModeTraits<2>; return EXPR; }    \
+    case 3: { using M = ModeTraits<3>; return EXPR; }    \
+    case 4: { using M = ModeTraits<4>; return EXPR; }    \
+    default: throw std::runtime_error("bad fast scatter mode"); \
+  }
+int fast_panel_cols(int mode) { RSDL_MODE_SWITCH(mode, M::PANEL) }
+int fast_ctas_per_sm(int mode) { RSDL_MODE_SWITCH(mode, M::MIN_CTAS) }
+int fast_tile_rows(int mode) { RSDL_MODE_SWITCH(mode, M::TILE) }
+int fast_src_itemsize(int mode) { RSDL_MODE_SWITCH(mode, M::SRC) }
 int fast_max_tile_rows() { return kMaxTileRows; }
 
 void launch_scatter_fast(const FastParams& p, int mode, int grid, cudaStream_t stream) {
@@ -734,6 +992,11 @@ void launch_scatter_fast(const FastParams& p, int mode, int grid, cudaStream_t s
     case 0: launch_fast_mode<0>(p, grid, stream); break;
     case 1: launch_fast_mode<1>(p, grid, stream); break;
     case 2: launch_fast_mode<2>(p, grid, stream); break;
+    case 3: launch_fast_mode<3>(p, grid, stream); break;
+    case 4:
+      if (p.kinds == nullptr) throw std::runtime_error("scatter mode 4 needs the per-column kinds table");
+      launch_fast_mode<4>(p, grid, stream);
+      break;
     default: throw std::runtime_error("bad fast scatter mode");
   }
   cudaError_t e = cudaGetLastError();

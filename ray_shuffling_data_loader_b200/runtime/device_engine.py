@@ -62,6 +62,10 @@ _FIELD_DTYPE = np.dtype([("src", "<u8"), ("src_code", "<u4"), ("dst_code", "<u4"
                          ("dst_off", "<u4"), ("width", "<u4")])
 
 
+# mode-4 conversion kinds (csrc/shuffle_kernels.cu): 8-byte source -> 4-byte field
+_KINDS_8_TO_4 = {(L.DT_I64, L.DT_F32): 0, (L.DT_F64, L.DT_F32): 1, (L.DT_I64, L.DT_I32): 2}
+
+
 def _align(x: int, a: int = _ALIGN) -> int:
     return (x + a - 1) // a * a
 
@@ -105,7 +109,8 @@ class DeviceShuffleEngine:
                  flag_timeout_s: float = 300.0, index=None,
                  device_index: Optional[int] = None, grid: Optional[int] = None,
                  process_group=None, force_generic: bool = False,
-                 use_tensor_map: bool = True, peer_alloc: Optional[str] = None):
+                 use_tensor_map: bool = True, peer_alloc: Optional[str] = None,
+                 backpressure: Optional[str] = None):
         import torch
         self.C = load_native()
         self.torch = torch
@@ -139,6 +144,16 @@ class DeviceShuffleEngine:
         self.flag_timeout_s = flag_timeout_s
         self.force_generic = force_generic
         self.use_tensor_map = use_tensor_map
+        # Slot reuse gate (the device analogue of the queue actor's epoch window,
+        # reference batch_queue.py:406-418): "stream" enqueues a wait kernel on
+        # the shuffle stream so epoch e+window's scatter starts the moment the
+        # last trainer's consumed flag lands - no host poll + launch latency
+        # between back-to-back shuffles; "host" polls from the driver thread.
+        self.backpressure = backpressure or os.environ.get("RSDL_BACKPRESSURE", "stream")
+        if self.backpressure not in ("stream", "host"):
+            raise ValueError("backpressure must be 'stream' or 'host'")
+        if exchange == "nccl":
+            self.backpressure = "host"      # collectives are enqueued by torch
         self.peer_alloc = peer_alloc or os.environ.get("RSDL_PEER_ALLOC", "symm")
         if self.peer_alloc not in ("symm", "ipc"):
             raise ValueError("peer_alloc must be 'symm' or 'ipc'")
@@ -291,8 +306,9 @@ class DeviceShuffleEngine:
                     gen[k] = (ptrs[i], f.src_code, f.dst_code, f.offset, f.width)
                 runs.append(gen)
             tables.append((fast_cols, runs))
+        kinds = np.array(self.fast_kinds or [0], dtype=np.uint8)
         blob = b"".join(_pad(a.tobytes()) + b"".join(_pad(g.tobytes()) for g in runs)
-                        for a, runs in tables)
+                        for a, runs in tables) + _pad(kinds.tobytes())
         self.desc_arena = C.device_malloc(max(256, len(blob)))
         self._desc_host, self._desc_host_ptr = pinned_array(C, (max(256, len(blob)),), np.uint8)
         self._desc_host[:len(blob)] = np.frombuffer(blob, dtype=np.uint8)
@@ -308,6 +324,7 @@ class DeviceShuffleEngine:
                 run_ptrs.append(off)
                 off += len(_pad(g.tobytes()))
             self.generic_fields_dev.append(run_ptrs)
+        self.fast_kinds_dev = off           # per-column conversion kinds (mode 4)
         if self.resident == "host":
             self.h2d_done = [C.event_create(False) for _ in range(self.num_src_bufs)]
             self.buf_free = [C.event_create(False) for _ in range(self.num_src_bufs)]
@@ -324,6 +341,8 @@ class DeviceShuffleEngine:
         lay = self.layout
         fields = self.src_fields
         self.fast_mode = -1
+        self.fast_kinds: List[int] = []
+        self.fast_write_end = 0
         self.fast_field_idx: List[int] = []
         self.wide_field_idx: List[int] = []
         nfast, fast_ranges = 0, []
@@ -368,25 +387,43 @@ class DeviceShuffleEngine:
         mode) - (0, [], -1) when the layout does not start with such a prefix."""
         lay, fields = self.layout, self.src_fields
         first = fields[0]
-        if first.width != 1 or L.itemsize(first.src_code) != 4 or first.offset != 0:
+        ssz = L.itemsize(first.src_code)
+        if first.width != 1 or ssz not in (4, 8) or first.offset != 0:
             return 0, [], -1
-        if first.dst_code == first.src_code:
-            mode = 0
-        elif first.src_code == L.DT_F32 and first.dst_code == L.DT_BF16:
-            mode = 1
-        elif (first.src_code == L.DT_F32 and first.dst_code == L.DT_FP8
-              and lay.scale_offset >= 0):
-            mode = 2
-        else:
-            return 0, [], -1
-        n, off = 0, 0
         dsz = L.itemsize(first.dst_code)
+        if ssz == 8:
+            # 8-byte sources (int64 / float64, the reference's DATA_SPEC): bit copy
+            # (mode 3) or per-column conversion to a 4-byte destination (mode 4)
+            mode = {8: 3, 4: 4}.get(dsz, -1)
+            if mode < 0:
+                return 0, [], -1
+
+            def same_class(f):
+                if L.itemsize(f.src_code) != 8 or L.itemsize(f.dst_code) != dsz:
+                    return False
+                return (f.dst_code == f.src_code if mode == 3
+                        else (f.src_code, f.dst_code) in _KINDS_8_TO_4)
+        else:
+            if first.dst_code == first.src_code:
+                mode = 0
+            elif first.src_code == L.DT_F32 and first.dst_code == L.DT_BF16:
+                mode = 1
+            elif (first.src_code == L.DT_F32 and first.dst_code == L.DT_FP8
+                  and lay.scale_offset >= 0):
+                mode = 2
+            else:
+                return 0, [], -1
+
+            def same_class(f):
+                return f.src_code == first.src_code and f.dst_code == first.dst_code
+        n, off = 0, 0
         for f in fields:
-            if (f.width != 1 or f.src_code != first.src_code
-                    or f.dst_code != first.dst_code or f.offset != off):
+            if f.width != 1 or not same_class(f) or f.offset != off:
                 break
             n += 1
             off += dsz
+        if mode == 4:
+            self.fast_kinds = [_KINDS_8_TO_4[(f.src_code, f.dst_code)] for f in fields[:n]]
         if n < 4:
             return 0, [], -1       # not worth a TMA launch
         fast_end = _align(off, 16)  # the kernel writes whole 16-byte groups
@@ -397,7 +434,10 @@ class DeviceShuffleEngine:
             scale_lo = lay.scale_offset if mode == 2 else lay.row_pitch
             if rest_lo < fast_end or (mode == 2 and rest_hi > scale_lo):
                 return 0, [], -1
-        ranges = [(0, fast_end)]
+        # with nothing behind the prefix the kernel also zero-fills the row's
+        # padding: every 32-byte sector of a row is then written whole
+        self.fast_write_end = fast_end if (rest or mode == 2) else lay.row_pitch
+        ranges = [(0, self.fast_write_end)]
         if mode == 2:               # plus the UE8M0 scale bytes after everything else
             ranges.append((lay.scale_offset, lay.scale_offset + (n + 31) // 32))
         return n, ranges, mode
@@ -493,7 +533,7 @@ class DeviceShuffleEngine:
             # tensor map (4 TMA box loads per tile instead of 64 bulk copies)
             ptrs = self.src_col_ptrs[buf]
             stride = self.col_bytes[0]
-            uniform = (self.use_tensor_map and self.tmap_mode != 0 and all(
+            uniform = (self.use_tensor_map and self.tmap_mode != 0 and self.fast_mode <= 2 and all(
                 ptrs[i] == ptrs[0] + i * stride for i in range(ncols)))
             C.scatter_fast(key=key_words, num_rows=plan.num_rows,
                            num_trainers=plan.num_trainers, cols=self.fast_cols_dev[buf],
@@ -506,7 +546,10 @@ class DeviceShuffleEngine:
                            col_base=ptrs[0] if uniform else 0,
                            col_stride=stride if uniform else 0,
                            rows_alloc=(stride // 4) if uniform else 0,
-                           tmap_mode=self.tmap_mode)
+                           tmap_mode=self.tmap_mode,
+                           kinds=self.fast_kinds_dev if self.fast_mode == 4 else 0,
+                           write_end=self.fast_write_end,
+                           sched=int(os.environ.get("RSDL_SCHED", "-1")))
             self.launches += 1
         for i in self.wide_field_idx:
             f = self.src_fields[i]
@@ -538,9 +581,14 @@ class DeviceShuffleEngine:
         with trace.span("ingest", epoch=epoch):
             self._ensure_ingested(epoch)
         slot = epoch % self.window
-        if epoch >= self.window:
-            # Back-pressure: every trainer must have released this slot's
-            # previous epoch before any source may overwrite it.
+        if epoch >= self.window and self.backpressure == "stream":
+            # Back-pressure, stream ordered: every trainer must have released
+            # this slot's previous epoch before any source may overwrite it.
+            C.wait_flags(self._consumed_ptr(self.rank, 0), plan.num_trainers,
+                         epoch - self.window + 1, int(self.flag_timeout_s * 1e9),
+                         self.arena + self.off_error, self.shuffle_stream)
+            self.launches += 1
+        elif epoch >= self.window:
             with trace.span("backpressure_wait", epoch=epoch):
                 lag = self._poll(self._consumed_ptr(self.rank, 0), plan.num_trainers,
                                  epoch - self.window + 1, self.flag_timeout_s)
@@ -672,6 +720,7 @@ class DeviceShuffleEngine:
                     lag = self._poll(self._produced_ptr(self.rank, slot, 0), self.world,
                                      epoch + 1, limit)
                 if lag >= 0:
+                    self.check_error()      # a device-side wait that gave up explains it
                     raise TimeoutError(
                         f"source rank {lag} did not deliver epoch {epoch} within {limit}s")
             state["done"] = True

@@ -132,10 +132,75 @@ def test_split_fast_features_generic_label(tmp_path_factory):
 
 def test_generic_data_spec_matches_golden(small_dataset):
     files, n = small_dataset
-    cpu, dev = _engines(files, L.dataframe_layout, 3)
+    cpu, dev = _engines(files, L.dataframe_layout, 3, force_generic=True)
     assert dev.fast_mode == -1
     try:
         _compare_epochs(cpu, dev)
+    finally:
+        dev.close(); cpu.close()
+
+
+@pytest.mark.parametrize("trainers,resident", [(1, "hbm"), (3, "hbm"), (2, "host")])
+def test_typed64_copy_data_spec_matches_golden(small_dataset, trainers, resident):
+    """DATA_SPEC rows in their native dtypes (21 x int64/float64 = what plain
+    ShufflingDataset shuffles): one TMA launch, mode 3 (8-byte bit copy)."""
+    files, n = small_dataset
+    opts = dict(resident=resident)
+    if resident == "host":
+        opts["stream_chunk_rows"] = 2500
+    cpu, dev = _engines(files, L.dataframe_layout, trainers, **opts)
+    assert dev.fast_mode == 3 and not dev.generic_field_idx
+    try:
+        _compare_epochs(cpu, dev)
+    finally:
+        dev.close(); cpu.close()
+
+
+def _int_files(tmp_path_factory, ncols, nrows=9_973):
+    from ray_shuffling_data_loader_b200.data_generation import generate_data
+    d = tmp_path_factory.mktemp(f"i{ncols}")
+    spec = {f"c{i}": ((-(1 << 40), 1 << 40, np.int64) if i % 3 else (0, 1, np.float64))
+            for i in range(ncols)}
+    files, _ = generate_data(nrows, 2, 2, 0.0, str(d), data_spec=spec, seed=ncols)
+    return files, list(spec)
+
+
+@pytest.mark.parametrize("ncols,trainers", [(21, 2), (70, 1), (33, 3), (5, 2)])
+def test_typed64_convert_matches_golden(tmp_path_factory, ncols, trainers):
+    """8-byte sources cast to 4-byte fields in the TMA kernel (mode 4):
+    int64 -> f32 (values beyond 2^24: round to nearest even), float64 -> f32,
+    int64 -> int32; more than 32 columns exercises the panel loop."""
+    files, names = _int_files(tmp_path_factory, ncols)
+
+    def fn(schema):
+        cols = []
+        for i, c in enumerate(names):
+            src = schema[c][0]
+            dst = L.DT_I32 if (src == L.DT_I64 and i % 5 == 1) else L.DT_F32
+            cols.append((c, src, dst, 1))
+        return L.build_layout(cols)
+    cpu, dev = _engines(files, fn, trainers)
+    assert dev.fast_mode == 4 and not dev.generic_field_idx
+    assert len(dev.fast_kinds) == ncols and set(dev.fast_kinds) <= {0, 1, 2}
+    try:
+        _compare_epochs(cpu, dev, epochs=(0, 1))
+    finally:
+        dev.close(); cpu.close()
+
+
+def test_typed64_prefix_then_generic_tail(small_dataset):
+    """The torch default on DATA_SPEC plus an int64 key kept as int64: the
+    float32 prefix rides mode 4, the 8-byte key the generic kernel."""
+    files, n = small_dataset
+
+    def fn(schema):
+        feats = [c for c in schema if c not in ("key",)]
+        return L.build_layout([(c, schema[c][0], L.DT_F32, 1) for c in feats]
+                              + [("key", L.DT_I64, L.DT_I64, 1)])
+    cpu, dev = _engines(files, fn, 2)
+    assert dev.fast_mode == 4 and len(dev.generic_field_idx) == 1
+    try:
+        _compare_epochs(cpu, dev, epochs=(0, 1))
     finally:
         dev.close(); cpu.close()
 
@@ -211,6 +276,21 @@ def test_stream_wait_mode(tmp_path_factory):
     cpu, dev = _engines(files, _f32_layout(cols), 1, wait_mode="stream")
     try:
         _compare_epochs(cpu, dev, epochs=(0, 1, 2))
+        dev.check_error()
+    finally:
+        dev.close(); cpu.close()
+
+
+@pytest.mark.parametrize("mode", ["stream", "host"])
+def test_backpressure_modes(tmp_path_factory, mode):
+    """Slot reuse beyond the window: the consumed-flag gate runs as a wait
+    kernel on the shuffle stream (default) or as a host poll."""
+    files = _float_files(tmp_path_factory, 64, name="bp" + mode)
+    cols = [f"f{i}" for i in range(63)] + ["labels"]
+    cpu, dev = _engines(files, _f32_layout(cols), 2, backpressure=mode)
+    assert dev.backpressure == mode
+    try:
+        _compare_epochs(cpu, dev, epochs=tuple(range(6)))
         dev.check_error()
     finally:
         dev.close(); cpu.close()
