@@ -83,6 +83,9 @@ def parse_args():
     p.add_argument("--exchange", choices=["p2p", "nccl"], default="p2p")
     p.add_argument("--feature-dtype", choices=["float32", "bfloat16", "fp8"], default="float32")
     p.add_argument("--peer-alloc", choices=["symm", "ipc"], default=None)
+    p.add_argument("--wait-mode", choices=["stream", "host"], default="stream",
+                   help="how a trainer waits for an epoch's produced flags: a wait kernel on its "
+                        "own stream (no host round trip) or a host poll")
     p.add_argument("--skip-e2e", action="store_true")
     p.add_argument("--keep-data", action="store_true")
     p.add_argument("--ref-steps-cap", type=int, default=None,
@@ -259,7 +262,7 @@ def make_dataset(args, files, rank, world, epochs, resident, torch, seed=2026092
     feature_columns = [f"f{i}" for i in range(args.cols - 1)]
     dt = {"float32": torch.float32, "bfloat16": torch.bfloat16,
           "fp8": getattr(torch, "float8_e4m3fn", None)}[args.feature_dtype]
-    opts = dict(resident=resident, exchange=args.exchange)
+    opts = dict(resident=resident, exchange=args.exchange, wait_mode=args.wait_mode)
     if args.peer_alloc:
         opts["peer_alloc"] = args.peer_alloc
     if resident == "host":
@@ -347,6 +350,7 @@ def run_ours(args):
                        "row_bytes": row_pitch, "batch_size": args.batch_size,
                        "seq_len": None, "parallelism": f"dp{world}",
                        "max_concurrent_epochs": 2, "exchange": args.exchange,
+                       "wait_mode": args.wait_mode,
                        "l2_policy": "inputs larger than L2 (3.2 GB/epoch/GPU)"},
             "batches_per_sec": value / args.batch_size,
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks,

@@ -23,6 +23,13 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <cctype>
+#include <fstream>
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
 #include "kernels.h"
 
 namespace py = pybind11;
@@ -232,6 +239,77 @@ class FlagPoller {
   std::mutex mu_;
 };
 
+// ---------------------------------------------------------------------------
+// NUMA placement: a rank's pinned staging memory and its host threads should
+// sit on the socket its GPU hangs off (HGX B200: GPUs 0-3 on node 0, 4-7 on
+// node 1) - with 8 ranks streaming from host memory at once, remote-socket
+// pinned buffers cost ~15% of the PCIe rate (profiles/README.md, e2e at N=8).
+// Ray's raylet does the equivalent per-node worker placement for the reference.
+// ---------------------------------------------------------------------------
+int gpu_numa_node(int device) {
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) return -1;
+  std::string id(bus);
+  std::transform(id.begin(), id.end(), id.begin(), [](unsigned char c) { return std::tolower(c); });
+  std::ifstream f("/sys/bus/pci/devices/" + id + "/numa_node");
+  int node = -1;
+  if (!(f >> node)) return -1;
+  return node;
+}
+
+// "0-31,64-95" -> cpu ids
+std::vector<int> parse_cpulist(const std::string& text) {
+  std::vector<int> cpus;
+  size_t i = 0;
+  while (i < text.size()) {
+    while (i < text.size() && !std::isdigit(static_cast<unsigned char>(text[i]))) ++i;
+    if (i >= text.size()) break;
+    int a = 0;
+    while (i < text.size() && std::isdigit(static_cast<unsigned char>(text[i]))) a = a * 10 + (text[i++] - '0');
+    int b = a;
+    if (i < text.size() && text[i] == '-') {
+      ++i;
+      b = 0;
+      while (i < text.size() && std::isdigit(static_cast<unsigned char>(text[i]))) b = b * 10 + (text[i++] - '0');
+    }
+    for (int c = a; c <= b && c < CPU_SETSIZE; ++c) cpus.push_back(c);
+  }
+  return cpus;
+}
+
+std::vector<int> numa_node_cpus(int node) {
+  std::ifstream f("/sys/devices/system/node/node" + std::to_string(node) + "/cpulist");
+  std::string line;
+  if (!std::getline(f, line)) return {};
+  return parse_cpulist(line);
+}
+
+// Restrict the calling thread (and every thread it creates afterwards) to the
+// node's CPUs, intersected with the CPUs it is currently allowed to use, and
+// prefer the node's memory for its allocations (first touch + MPOL_PREFERRED).
+// Returns the number of CPUs in the new mask, 0 when nothing was changed.
+int bind_thread_to_numa_node(int node) {
+  if (node < 0) return 0;
+  const std::vector<int> cpus = numa_node_cpus(node);
+  if (cpus.empty()) return 0;
+  cpu_set_t allowed, want;
+  CPU_ZERO(&allowed);
+  CPU_ZERO(&want);
+  if (sched_getaffinity(0, sizeof(allowed), &allowed) != 0) return 0;
+  int n = 0;
+  for (int c : cpus)
+    if (CPU_ISSET(c, &allowed)) { CPU_SET(c, &want); ++n; }
+  if (n == 0) return 0;                       // cgroup excludes that socket: leave as is
+  if (sched_setaffinity(0, sizeof(want), &want) != 0) return 0;
+#ifdef SYS_set_mempolicy
+  if (node < 64) {
+    unsigned long mask = 1ul << node;
+    syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, &mask, sizeof(mask) * 8 + 1);
+  }
+#endif
+  return n;
+}
+
 }  // namespace
 
 PYBIND11_MODULE(_C, m) {
@@ -252,6 +330,12 @@ PYBIND11_MODULE(_C, m) {
     check(cudaDeviceGetAttribute(&a, cudaDevAttrComputeCapabilityMajor, d), "attr");
     check(cudaDeviceGetAttribute(&b, cudaDevAttrComputeCapabilityMinor, d), "attr");
     return std::make_pair(a, b); });
+  m.def("gpu_numa_node", &gpu_numa_node,
+        "NUMA node of the GPU's PCIe root (-1 when the platform does not say)");
+  m.def("numa_node_cpus", &numa_node_cpus);
+  m.def("parse_cpulist", &parse_cpulist);
+  m.def("bind_thread_to_numa_node", &bind_thread_to_numa_node,
+        "pin the calling thread (and its future children) + memory policy to a NUMA node");
   m.def("mem_get_info", [] {
     size_t f, t; check(cudaMemGetInfo(&f, &t), "cudaMemGetInfo"); return std::make_pair(f, t); });
   m.def("can_access_peer", [](int a, int b) {

@@ -110,7 +110,7 @@ class DeviceShuffleEngine:
                  device_index: Optional[int] = None, grid: Optional[int] = None,
                  process_group=None, force_generic: bool = False,
                  use_tensor_map: bool = True, peer_alloc: Optional[str] = None,
-                 backpressure: Optional[str] = None):
+                 backpressure: Optional[str] = None, numa_bind: Optional[bool] = None):
         import torch
         self.C = load_native()
         self.torch = torch
@@ -122,6 +122,14 @@ class DeviceShuffleEngine:
         cc = self.C.compute_capability(device_index)
         if cc[0] < 10:
             raise RuntimeError(f"sm_100a kernels need a Blackwell GPU, found sm_{cc[0]}{cc[1]}")
+        # Put this rank's host side (decode threads, staging copies, pinned
+        # buffers) on the socket its GPU is attached to before anything is
+        # allocated. Only in one-process-per-GPU mode, and never widening the
+        # CPU set the process was given. RSDL_NUMA_BIND=0 disables it.
+        if numa_bind is None:
+            numa_bind = world > 1 and os.environ.get("RSDL_NUMA_BIND", "1") != "0"
+        self.numa_node = self.C.gpu_numa_node(device_index)
+        self.numa_cpus = self.C.bind_thread_to_numa_node(self.numa_node) if numa_bind else 0
         self.index = index or ingest.scan_files(filenames)
         self.plan = ShufflePlan(num_rows=self.index.num_rows, **plan_args)
         if world > 1 and self.plan.num_trainers != world:

@@ -69,3 +69,22 @@ def test_models_forward_backward():
     out.sum().backward()
     cnn = models.SmallConvNet()
     assert cnn(torch.rand(4, 1, 28, 28)).shape == (4, 10)
+
+
+def test_native_numa_helpers():
+    """The C++ runtime's NUMA placement helpers work without a GPU."""
+    import os
+    from ray_shuffling_data_loader_b200 import _C
+    assert _C.parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert _C.parse_cpulist("") == []
+    assert _C.gpu_numa_node(0) == -1 or _C.gpu_numa_node(0) >= 0
+    before = os.sched_getaffinity(0)
+    assert _C.bind_thread_to_numa_node(-1) == 0          # unknown node: untouched
+    assert os.sched_getaffinity(0) == before
+    cpus = _C.numa_node_cpus(0)
+    if cpus:
+        n = _C.bind_thread_to_numa_node(0)
+        after = os.sched_getaffinity(0)
+        assert after <= before                            # never widens the mask
+        assert n == 0 or n == len(after)
+        os.sched_setaffinity(0, before)
