@@ -86,6 +86,8 @@ def parse_args():
     p.add_argument("--wait-mode", choices=["stream", "host"], default="stream",
                    help="how a trainer waits for an epoch's produced flags: a wait kernel on its "
                         "own stream (no host round trip) or a host poll")
+    p.add_argument("--max-concurrent-epochs", type=int, default=2,
+                   help="epoch window (BASELINE config 3 compares 1 vs 2)")
     p.add_argument("--skip-e2e", action="store_true")
     p.add_argument("--keep-data", action="store_true")
     p.add_argument("--ref-steps-cap", type=int, default=None,
@@ -270,7 +272,7 @@ def make_dataset(args, files, rank, world, epochs, resident, torch, seed=2026092
     fp8 = args.feature_dtype == "fp8"
     return TorchShufflingDataset(
         files, epochs, world, args.batch_size, rank, num_reducers=world,
-        max_concurrent_epochs=2, feature_columns=feature_columns,
+        max_concurrent_epochs=args.max_concurrent_epochs, feature_columns=feature_columns,
         feature_types=[dt] * len(feature_columns), label_column="labels",
         label_type=dt if not fp8 else torch.float32, packed_features=True,
         fp8_block_scale=fp8, seed=seed, backend="cuda", queue_name=f"bench-{resident}", **opts)
@@ -349,7 +351,7 @@ def run_ours(args):
                        "rows": args.rows_per_gpu * world, "cols": args.cols,
                        "row_bytes": row_pitch, "batch_size": args.batch_size,
                        "seq_len": None, "parallelism": f"dp{world}",
-                       "max_concurrent_epochs": 2, "exchange": args.exchange,
+                       "max_concurrent_epochs": args.max_concurrent_epochs, "exchange": args.exchange,
                        "wait_mode": args.wait_mode,
                        "l2_policy": "inputs larger than L2 (3.2 GB/epoch/GPU)"},
             "batches_per_sec": value / args.batch_size,

@@ -165,6 +165,10 @@ def train_main(args):
         if world > 1:
             model = torch.nn.parallel.DistributedDataParallel(
                 model, device_ids=[ctx.local_rank] if use_cuda else None)
+            if use_cuda and os.environ.get("RSDL_EXAMPLE_GRAD_COMPRESSION") == "bf16":
+                # the reference's --fp16-allreduce (hvd.Compression.fp16, :188-190)
+                from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+                model.register_comm_hook(None, default_hooks.bf16_compress_hook)
         optimizer = torch.optim.SGD(model.parameters(), lr=args.lr * world,
                                     momentum=args.momentum)
 

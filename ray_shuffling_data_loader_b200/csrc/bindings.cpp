@@ -19,6 +19,7 @@
 #include <stdexcept>
 #include <string>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -31,6 +32,7 @@
 #include <unistd.h>
 
 #include "kernels.h"
+#include "perm.cuh"
 
 namespace py = pybind11;
 using rsdl::FastParams;
@@ -133,6 +135,28 @@ class HostPool {
     for (auto& t : workers_) t.join();
   }
   int size() const { return static_cast<int>(workers_.size()); }
+
+  // Run fn(begin, end) over [0, n) in `grain`-sized pieces on the workers; wait.
+  void parallel_for(size_t n, size_t grain, const std::function<void(size_t, size_t)>& fn) {
+    if (n == 0) return;
+    grain = std::max<size_t>(1, grain);
+    const size_t pieces = (n + grain - 1) / grain;
+    std::atomic<size_t> pending{pieces};
+    std::mutex done_mu;
+    std::condition_variable done_cv;
+    for (size_t b = 0; b < n; b += grain) {
+      const size_t e = std::min(n, b + grain);
+      submit([=, &fn, &pending, &done_mu, &done_cv] {
+        fn(b, e);
+        if (pending.fetch_sub(1) == 1) {
+          std::lock_guard<std::mutex> g(done_mu);
+          done_cv.notify_all();
+        }
+      });
+    }
+    std::unique_lock<std::mutex> lk(done_mu);
+    done_cv.wait(lk, [&] { return pending.load() == 0; });
+  }
 
   // Split [0, nbytes) into chunks, copy them on the workers, wait for all.
   void parallel_memcpy(void* dst, const void* src, size_t nbytes) {
@@ -238,6 +262,101 @@ class FlagPoller {
   cudaStream_t stream_ = nullptr;
   std::mutex mu_;
 };
+
+// ---------------------------------------------------------------------------
+// Host cast + pack: columnar table -> packed rows (the CPU backend's analogue
+// of the scatter kernels' epilogue; replaces one strided numpy assignment per
+// column, reference torch_dataset.py:204-236). Cast rules mirror
+// ops/layout.py::cast_column and the device's load_src / store_cast.
+// ---------------------------------------------------------------------------
+struct bf16_bits { uint16_t b; };
+struct f16_val { _Float16 v; };
+struct bool_val { uint8_t v; };
+
+template <typename S> struct Wide { using type = long long; };
+template <> struct Wide<float> { using type = float; };
+template <> struct Wide<double> { using type = double; };
+template <> struct Wide<bf16_bits> { using type = float; };
+template <> struct Wide<f16_val> { using type = float; };
+
+template <typename S> inline typename Wide<S>::type load_wide(const S& x) { return static_cast<typename Wide<S>::type>(x); }
+template <> inline float load_wide<bf16_bits>(const bf16_bits& x) {
+  uint32_t u = static_cast<uint32_t>(x.b) << 16; float f; std::memcpy(&f, &u, 4); return f; }
+template <> inline float load_wide<f16_val>(const f16_val& x) { return static_cast<float>(x.v); }
+template <> inline long long load_wide<bool_val>(const bool_val& x) { return x.v ? 1 : 0; }
+
+template <typename D, typename W> struct Conv {
+  static inline D run(W w) {
+    if constexpr (std::is_integral<D>::value && !std::is_integral<W>::value)
+      return static_cast<D>(static_cast<long long>(w));      // float -> int: via int64, then wrap
+    else
+      return static_cast<D>(w);
+  }
+};
+template <typename W> struct Conv<bf16_bits, W> {
+  static inline bf16_bits run(W w) {
+    const float f = static_cast<float>(w);
+    uint32_t u; std::memcpy(&u, &f, 4);
+    if (f != f) return bf16_bits{0x7FFF};                    // NaN canonicalised like CUDA
+    u = (u + 0x7FFFu + ((u >> 16) & 1u)) >> 16;              // round to nearest even
+    return bf16_bits{static_cast<uint16_t>(u)};
+  }
+};
+template <typename W> struct Conv<f16_val, W> {
+  static inline f16_val run(W w) { return f16_val{static_cast<_Float16>(w)}; }
+};
+template <typename W> struct Conv<bool_val, W> {
+  static inline bool_val run(W w) { return bool_val{static_cast<uint8_t>(w != 0 ? 1 : 0)}; }
+};
+
+template <typename S, typename D>
+void pack_field_block(const uint8_t* src_base, uint32_t width, uint8_t* out, uint32_t pitch,
+                      uint32_t dst_off, size_t r0, size_t r1) {
+  const S* src = reinterpret_cast<const S*>(src_base);
+  using W = typename Wide<S>::type;
+  for (size_t r = r0; r < r1; ++r) {
+    uint8_t* o = out + r * pitch + dst_off;
+    for (uint32_t w = 0; w < width; ++w) {
+      const D d = Conv<D, W>::run(load_wide<S>(src[r * width + w]));
+      std::memcpy(o + w * sizeof(D), &d, sizeof(D));         // fields are only dst-size aligned
+    }
+  }
+}
+
+template <typename S>
+bool pack_field_dst(uint32_t dst_code, const uint8_t* src, uint32_t width, uint8_t* out,
+                    uint32_t pitch, uint32_t off, size_t r0, size_t r1) {
+  switch (dst_code) {
+    case DT_U8:   pack_field_block<S, uint8_t>(src, width, out, pitch, off, r0, r1); return true;
+    case DT_I8:   pack_field_block<S, int8_t>(src, width, out, pitch, off, r0, r1); return true;
+    case DT_I16:  pack_field_block<S, int16_t>(src, width, out, pitch, off, r0, r1); return true;
+    case DT_I32:  pack_field_block<S, int32_t>(src, width, out, pitch, off, r0, r1); return true;
+    case DT_I64:  pack_field_block<S, long long>(src, width, out, pitch, off, r0, r1); return true;
+    case DT_F16:  pack_field_block<S, f16_val>(src, width, out, pitch, off, r0, r1); return true;
+    case DT_BF16: pack_field_block<S, bf16_bits>(src, width, out, pitch, off, r0, r1); return true;
+    case DT_F32:  pack_field_block<S, float>(src, width, out, pitch, off, r0, r1); return true;
+    case DT_F64:  pack_field_block<S, double>(src, width, out, pitch, off, r0, r1); return true;
+    case DT_BOOL: pack_field_block<S, bool_val>(src, width, out, pitch, off, r0, r1); return true;
+    default: return false;                                    // fp8: numpy golden path
+  }
+}
+
+bool pack_field(const FieldDev& f, uint8_t* out, uint32_t pitch, size_t r0, size_t r1) {
+  const uint8_t* s = f.src;
+  switch (f.src_code) {
+    case DT_U8:   return pack_field_dst<uint8_t>(f.dst_code, s, f.width, out, pitch, f.dst_off, r0, r1);
+    case DT_I8:   return pack_field_dst<int8_t>(f.dst_code, s, f.width, out, pitch, f.dst_off, r0, r1);
+    case DT_I16:  return pack_field_dst<int16_t>(f.dst_code, s, f.width, out, pitch, f.dst_off, r0, r1);
+    case DT_I32:  return pack_field_dst<int32_t>(f.dst_code, s, f.width, out, pitch, f.dst_off, r0, r1);
+    case DT_I64:  return pack_field_dst<long long>(f.dst_code, s, f.width, out, pitch, f.dst_off, r0, r1);
+    case DT_F16:  return pack_field_dst<f16_val>(f.dst_code, s, f.width, out, pitch, f.dst_off, r0, r1);
+    case DT_BF16: return pack_field_dst<bf16_bits>(f.dst_code, s, f.width, out, pitch, f.dst_off, r0, r1);
+    case DT_F32:  return pack_field_dst<float>(f.dst_code, s, f.width, out, pitch, f.dst_off, r0, r1);
+    case DT_F64:  return pack_field_dst<double>(f.dst_code, s, f.width, out, pitch, f.dst_off, r0, r1);
+    case DT_BOOL: return pack_field_dst<bool_val>(f.dst_code, s, f.width, out, pitch, f.dst_off, r0, r1);
+    default: return false;
+  }
+}
 
 // ---------------------------------------------------------------------------
 // NUMA placement: a rank's pinned staging memory and its host threads should
@@ -571,6 +690,71 @@ PYBIND11_MODULE(_C, m) {
              py::gil_scoped_release r;
              self.parallel_memcpy(as_ptr<void>(dst), as_ptr<const void>(src), n);
            });
+  // ---- host shuffle (backend="cpu"): the same bijection, on the worker pool ----
+  // The CPU engine's per-epoch work (reference shuffle_map + shuffle_reduce,
+  // shuffle.py:129-200) as native code: perm.cuh is shared with the kernels, so
+  // host and device agree bit for bit by construction.
+  m.def("host_pack_rows",
+        [](HostPool& pool, uintptr_t fields, uint32_t num_fields, uint64_t num_rows,
+           uint32_t row_pitch, uintptr_t out) {
+          // `fields`: host array of FieldDev (src = host column pointer)
+          const FieldDev* f = as_ptr<const FieldDev>(fields);
+          for (uint32_t i = 0; i < num_fields; ++i)
+            if (f[i].dst_code == DT_FP8 || f[i].src_code == DT_FP8)
+              throw std::runtime_error("host_pack_rows: fp8 fields take the numpy path");
+          uint8_t* o = as_ptr<uint8_t>(out);
+          std::atomic<bool> ok{true};
+          py::gil_scoped_release r;
+          pool.parallel_for(num_rows, 4096, [&](size_t b, size_t e) {
+            std::memset(o + b * row_pitch, 0, (e - b) * static_cast<size_t>(row_pitch));
+            for (uint32_t i = 0; i < num_fields; ++i)
+              if (!pack_field(f[i], o, row_pitch, b, e)) ok = false;
+          });
+          if (!ok) throw std::runtime_error("host_pack_rows: unsupported dtype code");
+        },
+        py::arg("pool"), py::arg("fields"), py::arg("num_fields"), py::arg("num_rows"),
+        py::arg("row_pitch"), py::arg("out"));
+  m.def("host_perm_positions",
+        [](HostPool& pool, const std::vector<uint64_t>& key, uint64_t num_rows,
+           uint32_t num_trainers, uint64_t global_offset, uint64_t n_local, uintptr_t trainer,
+           uintptr_t slot) {
+          const PermKeyDev k = make_key(key);
+          const PlanDev plan = make_plan(num_rows, num_trainers);
+          int32_t* tr = as_ptr<int32_t>(trainer);
+          long long* sl = as_ptr<long long>(slot);
+          py::gil_scoped_release r;
+          pool.parallel_for(n_local, 1 << 16, [&](size_t b, size_t e) {
+            for (size_t i = b; i < e; ++i) {
+              uint32_t t; unsigned long long s;
+              rsdl_position_to_dest(rsdl_permute(global_offset + i, k), plan, &t, &s);
+              tr[i] = static_cast<int32_t>(t);
+              sl[i] = static_cast<long long>(s);
+            }
+          });
+        },
+        py::arg("pool"), py::arg("key"), py::arg("num_rows"), py::arg("num_trainers"),
+        py::arg("global_offset"), py::arg("n_local"), py::arg("trainer"), py::arg("slot"));
+  m.def("host_scatter_rows",
+        [](HostPool& pool, const std::vector<uint64_t>& key, uint64_t num_rows,
+           uint32_t num_trainers, uintptr_t packed, uint32_t row_pitch, uint64_t global_offset,
+           uint64_t n_local, const std::vector<uintptr_t>& dst) {
+          if (dst.size() != num_trainers) throw std::runtime_error("one destination per trainer");
+          const PermKeyDev k = make_key(key);
+          const PlanDev plan = make_plan(num_rows, num_trainers);
+          const uint8_t* src = as_ptr<const uint8_t>(packed);
+          py::gil_scoped_release r;
+          pool.parallel_for(n_local, 1 << 14, [&](size_t b, size_t e) {
+            for (size_t i = b; i < e; ++i) {
+              uint32_t t; unsigned long long s;
+              rsdl_position_to_dest(rsdl_permute(global_offset + i, k), plan, &t, &s);
+              if (dst[t] == 0) continue;            // trainer not served by this process
+              std::memcpy(as_ptr<uint8_t>(dst[t]) + s * row_pitch, src + i * row_pitch, row_pitch);
+            }
+          });
+        },
+        py::arg("pool"), py::arg("key"), py::arg("num_rows"), py::arg("num_trainers"),
+        py::arg("packed"), py::arg("row_pitch"), py::arg("global_offset"), py::arg("n_local"),
+        py::arg("dst"));
   py::class_<FlagPoller>(m, "FlagPoller")
       .def(py::init<>())
       .def("wait",

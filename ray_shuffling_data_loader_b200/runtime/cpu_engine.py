@@ -30,6 +30,44 @@ from ray_shuffling_data_loader_b200.runtime import ingest
 from ray_shuffling_data_loader_b200.runtime.chunks import EpochBuffer
 
 
+def _load_native():
+    """The C++ runtime (``csrc/bindings.cpp``: worker pool + the shared
+    ``perm.cuh`` bijection) when it has been built; ``None`` keeps the pure
+    numpy path, which is also the golden model of the native one."""
+    if os.environ.get("RSDL_CPU_NATIVE", "1") == "0":
+        return None
+    try:
+        from ray_shuffling_data_loader_b200 import _C
+        return _C if hasattr(_C, "host_scatter_rows") else None
+    except ImportError:
+        return None
+
+
+_FIELD_DTYPE = np.dtype([("src", "<u8"), ("src_code", "<u4"), ("dst_code", "<u4"),
+                         ("dst_off", "<u4"), ("width", "<u4")])
+
+
+def native_pack_rows(C, pool, columns: Dict[str, np.ndarray], layout: L.RowLayout) -> np.ndarray:
+    """``L.pack_rows`` (all rows, in order) on the C++ worker pool: one pass
+    over row blocks instead of one strided numpy assignment per column.
+    Layouts with fp8 fields keep the numpy path (block scaling lives there)."""
+    if layout.scale_offset >= 0 or any(L.DT_FP8 in (f.src_code, f.dst_code) for f in layout.fields):
+        return L.pack_rows(columns, layout)
+    n = len(columns[layout.fields[0].name])
+    out = np.empty((n, layout.row_pitch), dtype=np.uint8)
+    desc = np.zeros(len(layout.fields), dtype=_FIELD_DTYPE)
+    keep = []
+    for i, f in enumerate(layout.fields):
+        col = np.ascontiguousarray(columns[f.name], dtype=L.numpy_storage_dtype(f.src_code))
+        if col.size != n * f.width:
+            raise ValueError(f"column {f.name}: {col.shape} does not hold {n} x {f.width}")
+        keep.append(col)
+        desc[i] = (col.ctypes.data, f.src_code, f.dst_code, f.offset, f.width)
+    if n:
+        C.host_pack_rows(pool, desc.ctypes.data, len(desc), n, layout.row_pitch, out.ctypes.data)
+    return out
+
+
 class CpuShuffleEngine:
     """See module docstring. ``world``/``rank`` describe cooperating processes
     (gloo); with ``world == 1`` this process serves every trainer."""
@@ -39,8 +77,12 @@ class CpuShuffleEngine:
     def __init__(self, filenames: Sequence[str], plan_args: dict,
                  layout_fn, seed: int, rank: int = 0, world: int = 1,
                  stats_collector=None, num_threads: Optional[int] = None,
-                 process_group=None, index: Optional[ingest.DatasetIndex] = None):
+                 process_group=None, index: Optional[ingest.DatasetIndex] = None,
+                 native: Optional[bool] = None):
         self.index = index or ingest.scan_files(filenames)
+        self.C = _load_native() if native in (None, True) else None
+        if native is True and self.C is None:
+            raise RuntimeError("native=True but ray_shuffling_data_loader_b200._C is not built")
         self.plan = ShufflePlan(num_rows=self.index.num_rows, **plan_args)
         if world > 1 and self.plan.num_trainers != world:
             raise ValueError("distributed mode needs num_trainers == world size")
@@ -54,6 +96,7 @@ class CpuShuffleEngine:
         self.local_trainers: List[int] = ([rank] if world > 1
                                           else list(range(self.plan.num_trainers)))
         self._pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="cpu-shuffle")
+        self._host_pool = self.C.HostPool(self.num_threads) if self.C is not None else None
         self._packed: Optional[np.ndarray] = None
         self._lock = threading.Lock()
         self._ingest_reads: List[float] = []
@@ -80,7 +123,10 @@ class CpuShuffleEngine:
             table = ingest.load_table(self.index, lo, hi, columns=self.layout.names,
                                       num_threads=self.num_threads)
             # Cast + pack once; every epoch is then a pure row permutation.
-            self._packed = L.pack_rows(table.columns, self.layout)
+            if self.C is not None:
+                self._packed = native_pack_rows(self.C, self._host_pool, table.columns, self.layout)
+            else:
+                self._packed = L.pack_rows(table.columns, self.layout)
             self._offset = lo
             dur = timeit.default_timer() - t0
             reads = table.read_durations or [0.0]
@@ -113,15 +159,32 @@ class CpuShuffleEngine:
                     self.stats.reduce_start(epoch)
             key = perm.make_key(self.plan.num_rows, self.seed, epoch)
             n_local = self._packed.shape[0]
-            gidx = np.arange(self._offset, self._offset + n_local, dtype=np.uint64)
-            pos = perm.permute(gidx, key)
-            trainer, slot = self.plan.position_to_trainer(pos)
-            if self.world == 1:
-                for t, buf in buffers.items():
-                    sel = np.nonzero(trainer == t)[0]
-                    buf.data[slot[sel]] = self._packed[sel]
+            if self.C is not None and n_local:
+                # native path: pi_e + scatter on the C++ worker pool, GIL released
+                words = list(key.as_words())
+                T = self.plan.num_trainers
+                if self.world == 1:
+                    dst = [buffers[t].data.ctypes.data if t in buffers else 0 for t in range(T)]
+                    self.C.host_scatter_rows(self._host_pool, words, self.plan.num_rows, T,
+                                             self._packed.ctypes.data, self.layout.row_pitch,
+                                             self._offset, n_local, dst)
+                else:
+                    trainer = np.empty(n_local, dtype=np.int32)
+                    slot = np.empty(n_local, dtype=np.int64)
+                    self.C.host_perm_positions(self._host_pool, words, self.plan.num_rows, T,
+                                               self._offset, n_local, trainer.ctypes.data,
+                                               slot.ctypes.data)
+                    self._exchange(trainer, slot, buffers[self.rank])
             else:
-                self._exchange(trainer, slot, buffers[self.rank])
+                gidx = np.arange(self._offset, self._offset + n_local, dtype=np.uint64)
+                pos = perm.permute(gidx, key)
+                trainer, slot = self.plan.position_to_trainer(pos)
+                if self.world == 1:
+                    for t, buf in buffers.items():
+                        sel = np.nonzero(trainer == t)[0]
+                        buf.data[slot[sel]] = self._packed[sel]
+                else:
+                    self._exchange(trainer, slot, buffers[self.rank])
             dur = timeit.default_timer() - t0
             if self.stats is not None:
                 for _ in range(self.plan.num_reducers):
@@ -171,4 +234,5 @@ class CpuShuffleEngine:
             from ray_shuffling_data_loader_b200 import stats as stats_mod
             stats_mod.unregister_bytes_used_source(self._bytes_fn)
             self._pool.shutdown(wait=True)
+            self._host_pool = None
             self._packed = None

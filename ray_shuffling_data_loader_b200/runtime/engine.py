@@ -58,6 +58,6 @@ def make_engine(filenames: Sequence[str], *, num_trainers: int, num_reducers: in
                                    **options)
     from ray_shuffling_data_loader_b200.runtime.cpu_engine import CpuShuffleEngine
     cpu_opts = {k: v for k, v in options.items()
-                if k in ("num_threads", "process_group", "index")}
+                if k in ("num_threads", "process_group", "index", "native")}
     return CpuShuffleEngine(filenames, plan_args, layout_fn, seed, rank=rank,
                             world=world, stats_collector=stats_collector, **cpu_opts)

@@ -1,0 +1,97 @@
+"""The C++ host runtime (csrc/bindings.cpp) against the numpy golden: the
+native CPU shuffle must reproduce the pure-numpy engine byte for byte, because
+both share the definition of the bijection (perm.cuh == ops/perm.py)."""
+import numpy as np
+import pytest
+
+from ray_shuffling_data_loader_b200.ops import layout as L
+from ray_shuffling_data_loader_b200.ops import perm
+from ray_shuffling_data_loader_b200.ops.plan import ShufflePlan
+
+_C = pytest.importorskip("ray_shuffling_data_loader_b200._C")
+
+
+@pytest.mark.parametrize("n,T,off,cnt", [(1000, 1, 0, 1000), (100_003, 8, 12_345, 40_000),
+                                         (7, 3, 0, 7), (1 << 20, 5, 999, 70_000), (1, 1, 0, 1)])
+def test_host_perm_positions_match_numpy(n, T, off, cnt):
+    pool = _C.HostPool(3)
+    for epoch in (0, 3):
+        key = perm.make_key(n, 77, epoch)
+        plan = ShufflePlan(n, T, T, 10)
+        tr = np.empty(cnt, dtype=np.int32)
+        sl = np.empty(cnt, dtype=np.int64)
+        _C.host_perm_positions(pool, list(key.as_words()), n, T, off, cnt,
+                               tr.ctypes.data, sl.ctypes.data)
+        pos = perm.permute(np.arange(off, off + cnt, dtype=np.uint64), key)
+        t_ref, s_ref = plan.position_to_trainer(pos)
+        assert np.array_equal(tr, t_ref) and np.array_equal(sl, s_ref)
+
+
+@pytest.mark.parametrize("trainers", [1, 3])
+def test_native_cpu_engine_equals_numpy_engine(small_dataset, trainers):
+    from ray_shuffling_data_loader_b200.runtime.cpu_engine import CpuShuffleEngine
+    files, n = small_dataset
+    plan_args = dict(num_trainers=trainers, num_reducers=4, batch_size=500, drop_last=False)
+    gold = CpuShuffleEngine(files, plan_args, L.dataframe_layout, 11, native=False)
+    fast = CpuShuffleEngine(files, plan_args, L.dataframe_layout, 11, native=True, num_threads=4)
+    assert gold.C is None and fast.C is not None
+    try:
+        for epoch in range(3):
+            gb, fb = gold.start_epoch(epoch), fast.start_epoch(epoch)
+            for t in range(trainers):
+                gb[t].wait(60); fb[t].wait(60)
+                assert np.array_equal(gb[t].data, fb[t].data), (epoch, t)
+    finally:
+        gold.close(); fast.close()
+
+
+def test_host_scatter_skips_trainers_not_served():
+    """dst == 0 for a trainer means "not mine": rows for it are left alone."""
+    pool = _C.HostPool(2)
+    n, T, pitch = 5000, 2, 16
+    key = perm.make_key(n, 5, 1)
+    packed = np.arange(n * pitch, dtype=np.uint8).reshape(n, pitch)
+    plan = ShufflePlan(n, T, T, 10)
+    out1 = np.zeros((plan.trainer_rows(1), pitch), dtype=np.uint8)
+    _C.host_scatter_rows(pool, list(key.as_words()), n, T, packed.ctypes.data, pitch, 0, n,
+                         [0, out1.ctypes.data])
+    tr, sl = plan.position_to_trainer(perm.permute(np.arange(n, dtype=np.uint64), key))
+    want = np.zeros_like(out1)
+    want[sl[tr == 1]] = packed[tr == 1]
+    assert np.array_equal(out1, want)
+
+
+def test_native_pack_rows_all_casts_match_numpy_golden():
+    """Every (src, dst) cast the packed-row layout supports, list columns and
+    odd field alignment: C++ pack == ops/layout.py::pack_rows."""
+    from ray_shuffling_data_loader_b200.runtime.cpu_engine import native_pack_rows
+    rng = np.random.default_rng(0)
+    n = 10_007
+    cols = {
+        "i64": rng.integers(-(1 << 40), 1 << 40, n, dtype=np.int64),
+        "i32": rng.integers(-(1 << 20), 1 << 20, n, dtype=np.int32),
+        "u8": rng.integers(0, 255, n, dtype=np.uint8),
+        "f32": (rng.random(n, dtype=np.float32) - 0.5) * 1000,
+        "f64": (rng.random(n) - 0.5) * 1e6,
+        "f16": rng.random(n).astype(np.float16),
+        "b": rng.integers(0, 2, n).astype(np.bool_),
+        "img": rng.random((n, 5), dtype=np.float32),
+    }
+    codes = {"i64": L.DT_I64, "i32": L.DT_I32, "u8": L.DT_U8, "f32": L.DT_F32, "f64": L.DT_F64,
+             "f16": L.DT_F16, "b": L.DT_BOOL, "img": L.DT_F32}
+    spec = []
+    for name, src in codes.items():
+        for dst in (L.DT_F32, L.DT_BF16, L.DT_F16, L.DT_F64, L.DT_I64, L.DT_I32, L.DT_I16,
+                    L.DT_U8, L.DT_BOOL):
+            if name in ("f32", "f64", "f16", "img") and dst in (L.DT_I16, L.DT_U8):
+                continue                      # out-of-range float -> small int is UB in both
+            spec.append((name, src, dst, 5 if name == "img" else 1))
+    layout = L.build_layout(spec)
+    pool = _C.HostPool(4)
+    got = native_pack_rows(_C, pool, cols, layout)
+    want = L.pack_rows(cols, layout)
+    for f in layout.fields:
+        a, b = L.unpack_field(got, f), L.unpack_field(want, f)
+        assert np.array_equal(a, b, equal_nan=False) or np.array_equal(
+            a.view(np.uint8), b.view(np.uint8)), (f.name, f.src_code, f.dst_code)
+    assert np.array_equal(got, want)          # padding bytes are zero in both

@@ -54,6 +54,25 @@ def test_example_trains_and_reports_wait_times(tmp_path):
     assert out.count("stats over 8 steps") == 2       # 12000 / 1500 batches per epoch
 
 
+@pytest.mark.timeout(300)
+def test_self_launching_example_with_reference_flags(tmp_path):
+    """examples/horovod/ray_torch_shuffle.py: the reference's CLI, spawning its
+    own workers (2 gloo ranks here) like the RayExecutor launcher did."""
+    out = _run(["examples/horovod/ray_torch_shuffle.py", "--num-workers", "2", "--no-cuda",
+                "--num-rows", "16000", "--num-files", "4", "--num-columns", "8",
+                "--batch-size", "2000", "--epochs", "2", "--num-reducers", "4",
+                "--mock-train-step-time", "0.001", "--cpus-per-worker", "2",
+                "--data-dir", str(tmp_path)])
+    assert "--cpus-per-worker only apply to Ray/Horovod" in out
+    assert out.count("Done consuming batches on worker") == 2
+    assert out.count("stats over 4 steps") == 4       # 2 workers x 2 epochs, 8000 rows each
+    bad = subprocess.run([sys.executable, "examples/horovod/ray_torch_shuffle.py",
+                          "--num-workers", "2", "--num-hosts", "1"], cwd=ROOT,
+                         env=dict(os.environ, PYTHONPATH=ROOT), capture_output=True, text=True,
+                         timeout=120)
+    assert bad.returncode != 0 and "either --num-workers or" in bad.stderr
+
+
 def test_models_forward_backward():
     import torch
     from ray_shuffling_data_loader_b200 import models
