@@ -7,18 +7,20 @@
 // (dataset.py:144-168) and per-column torch.as_tensor (torch_dataset.py:209-235)
 // - is one kernel here:
 //
-//   scatter_tma_kernel    TMA bulk loads of a [cols x TILE_ROWS] tile of the
-//                         local *columnar* table into padded shared memory,
+//   scatter_tma_kernel    warp-specialised, one CTA per SM: loader warps move a
+//                         [cols x TILE_ROWS] tile of the local *columnar* table
+//                         into padded shared memory with TMA bulk copies; index
+//                         warps evaluate the Feistel bijection for the tile's rows
+//                         and publish each row's final address - (trainer, slot)
+//                         in local or *peer* HBM (VMM / CUDA-IPC mapped, NVLink 5
+//                         / NVSwitch) - through shared memory; consumer warps do a
 //                         conflict-free 4x4 register transposition to row-major,
-//                         optional cast (bf16 / block-scaled e4m3), and 128 B
-//                         coalesced vector stores of every row straight into its
-//                         final (trainer, slot) - a local or a *peer* HBM address
-//                         (CUDA-IPC mapped, NVLink 5 / NVSwitch). The row's
-//                         destination comes from the Feistel bijection, computed
-//                         once per tile by the producer warp and shared with the
-//                         consumer warps through shared memory.
-//   scatter_generic_kernel mixed dtypes / list columns / arbitrary casts
-//                         (the DATA_SPEC schema), staged through shared memory.
+//                         the cast (f32 | bf16 | block-scaled e4m3 | int64/float64
+//                         copy | int64/float64 -> f32/int32) and 128 B coalesced
+//                         vector stores of every row straight to that address.
+//   scatter_wide_kernel   list-valued columns (images): permuted row copy + cast.
+//   scatter_generic_kernel everything else (1-2-byte sources, exotic casts),
+//                         staged through shared memory.
 //
 // No NCCL call and no intermediate buffer sit on this path; NCCL all_to_all is
 // only the baseline (parallel/nccl_baseline.py).
@@ -48,11 +50,10 @@
 #ifndef RSDL_PANEL_F32
 #define RSDL_PANEL_F32 64
 #endif
-// Consumer warp groups (8 warps each) that take alternate pipeline stages. One
-// group has 2 warps per SM sub-partition: enough for 64 x 4-byte columns (the
-// tile is 32 KB of work), but latency bound for narrow tables - DATA_SPEC's 21
-// columns leave each consumer warp one short dependent chain per tile
-// (profiles/scatter_typed64_v7_mode4_21cols.md: stall_wait + branch_resolving).
+// Consumer warp groups (8 warps each) that take alternate pipeline stages.
+// Measured (profiles/kbench_v8/v10/v20.jsonl): a second group changes nothing
+// for any mode or width - the consumers are never the limiter once the row
+// padding is zero-filled - so one group is the default; kept as an A/B knob.
 #ifndef RSDL_CGROUPS_F32
 #define RSDL_CGROUPS_F32 1
 #endif
@@ -193,9 +194,11 @@ constexpr int kConsumerWarps = 8;
 constexpr int kMaxTileRows = 256;
 
 template <int MODE> struct ModeTraits;
-// TILE rows per tile: 256 makes every 1-D bulk copy 1 KB (the TMA unit retires
-// roughly one op per ~46 cycles per SM, so 512-byte copies cap the read rate near
-// 3 TB/s); INDEX_WARPS x 32 threads each own TILE/(32*INDEX_WARPS) rows' pointers.
+// TILE rows per tile x PANEL columns per stage. The TMA unit retires roughly one
+// bulk copy per ~46 cycles per SM, so 512-byte copies (128-row f32 tiles) cap the
+// read rate near 3 TB/s = the 90 % of the HBM copy peak the f32 kernel reaches;
+// 256-row tiles (1 KB copies), 32-column panels and 3-8 stages were all measured
+// and are within 2 % (profiles/kbench_v14.jsonl), so the smallest tile stays.
 // SRC = source itemsize in bytes. Modes 3/4 take 8-byte source columns (int64 /
 // float64: the reference's DATA_SPEC schema, data_generation.py:56-77) - mode 3
 // copies them bit for bit (plain ShufflingDataset rows), mode 4 converts every

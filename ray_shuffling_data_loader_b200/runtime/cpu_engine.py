@@ -147,6 +147,8 @@ class CpuShuffleEngine:
             data = np.empty((rows, layout.row_pitch), dtype=np.uint8)
             buffers[t] = EpochBuffer(epoch, t, rows, layout, data, "cpu")
             self._bytes_in_flight += data.nbytes
+        from ray_shuffling_data_loader_b200 import stats as stats_mod
+        stats_mod.note_bytes_in_use(self.bytes_in_use())
         self._pool.submit(self._run_epoch, epoch, buffers)
         return buffers
 

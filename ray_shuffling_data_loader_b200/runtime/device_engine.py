@@ -198,6 +198,7 @@ class DeviceShuffleEngine:
         self._setup_sources()
         self._bytes_fn = self.bytes_in_use
         stats_mod.register_bytes_used_source(self._bytes_fn)
+        stats_mod.note_bytes_in_use(self.bytes_in_use())
 
     # ------------------------------------------------------------------
     # memory

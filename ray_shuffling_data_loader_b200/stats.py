@@ -308,6 +308,18 @@ def unregister_bytes_used_source(fn: Callable[[], int]) -> None:
         _ARENA_BYTES_FNS.remove(fn)
 
 
+_PEAK_SINCE_SAMPLE = [0]
+
+
+def note_bytes_in_use(nbytes: int) -> None:
+    """High-water mark between two samples: engines call this when they
+    allocate, so a trial shorter than ``utilization_sample_period`` (an epoch is
+    milliseconds here, the reference sampled plasma every 5 s,
+    ``stats.py:258-279``) still reports what it held."""
+    if nbytes > _PEAK_SINCE_SAMPLE[0]:
+        _PEAK_SINCE_SAMPLE[0] = int(nbytes)
+
+
 def default_bytes_used() -> int:
     total = 0
     for fn in list(_ARENA_BYTES_FNS):
@@ -315,7 +327,8 @@ def default_bytes_used() -> int:
             total += int(fn())
         except Exception:
             pass
-    return total
+    peak, _PEAK_SINCE_SAMPLE[0] = _PEAK_SINCE_SAMPLE[0], 0
+    return max(total, peak)
 
 
 def collect_store_stats(store_stats, done_event, utilization_sample_period,
@@ -328,6 +341,9 @@ def collect_store_stats(store_stats, done_event, utilization_sample_period,
             print(f"shuffle store in use: {human_readable_size(used)}")
         store_stats.append((get_time, StoreSample(used)))
         is_done = done_event.wait(timeout=utilization_sample_period)
+    # one last sample: picks up the high-water mark of a trial that ended
+    # before the first period elapsed
+    store_stats.append((timeit.default_timer(), StoreSample(bytes_used_fn())))
 
 
 #

@@ -281,6 +281,28 @@ def test_stream_wait_mode(tmp_path_factory):
         dev.close(); cpu.close()
 
 
+@pytest.mark.parametrize("sched", ["0", "1"])
+def test_producer_schedules_agree(tmp_path_factory, small_dataset, monkeypatch, sched):
+    """Both producer schedules of the TMA kernel (loader warps + tile-per-warp
+    index vs cooperative index warps that also load) must give the golden bytes,
+    for 4-byte and 8-byte sources, single- and multi-panel tables."""
+    monkeypatch.setenv("RSDL_SCHED", sched)
+    files = _float_files(tmp_path_factory, 150, name="sc" + sched)
+    cols = [f"f{i}" for i in range(149)] + ["labels"]
+    cpu, dev = _engines(files, _f32_layout(cols), 3)
+    try:
+        _compare_epochs(cpu, dev, epochs=(0, 1))
+    finally:
+        dev.close(); cpu.close()
+    dfiles, _ = small_dataset
+    cpu, dev = _engines(dfiles, L.dataframe_layout, 2)
+    assert dev.fast_mode == 3
+    try:
+        _compare_epochs(cpu, dev, epochs=(0, 1))
+    finally:
+        dev.close(); cpu.close()
+
+
 @pytest.mark.parametrize("mode", ["stream", "host"])
 def test_backpressure_modes(tmp_path_factory, mode):
     """Slot reuse beyond the window: the consumed-flag gate runs as a wait
