@@ -1,6 +1,8 @@
 """Synthetic Parquet generator (C14) - with the reference's quirks fixed."""
 import os
 
+import pytest
+
 import numpy as np
 import pandas as pd
 import pyarrow.parquet as pq
@@ -52,3 +54,23 @@ def test_ingest_row_ranges(tmp_path):
     assert np.array_equal(t.columns["labels"], full["labels"].to_numpy()[150:777])
     empty = ingest.load_table(index, 10, 10, columns=["key"])
     assert empty.num_rows == 0 and len(empty.columns["key"]) == 0
+
+
+def test_row_group_skew(tmp_path):
+    """max_row_group_skew (asserted to be 0.0 upstream, data_generation.py:15):
+    sizes vary within +-skew of the mean, totals and keys are untouched."""
+    import pyarrow.parquet as pq
+    from ray_shuffling_data_loader_b200.data_generation import generate_data
+    files, _ = generate_data(40_000, 2, 8, 0.5, str(tmp_path), seed=3)
+    keys = []
+    for f in files:
+        md = pq.ParquetFile(f).metadata
+        sizes = [md.row_group(i).num_rows for i in range(md.num_row_groups)]
+        assert len(sizes) == 8 and sum(sizes) == 20_000
+        assert len(set(sizes)) > 1
+        mean = 20_000 / 8
+        assert min(sizes) >= mean * 0.5 / 1.5 - 1 and max(sizes) <= mean * 1.5 / 0.5 + 1
+        keys.append(pq.read_table(f, columns=["key"]).column("key").to_numpy())
+    assert np.array_equal(np.concatenate(keys), np.arange(40_000))
+    with pytest.raises(ValueError):
+        generate_data(100, 1, 2, 1.5, str(tmp_path / "bad"))
