@@ -717,7 +717,13 @@ class DeviceShuffleEngine:
                 return
             self.C.set_device(self.device_index)
             if self.wait_mode == "stream":
-                # Device-side wait on the consumer's stream: no host sync.
+                # Device-side wait on the consumer's stream: no host sync. A wait
+                # kernel that gave up (dead peer) only sets the error word, so
+                # look at it once per epoch - an unordered 4-byte read on the
+                # poller's stream - and fail within an epoch instead of feeding
+                # the trainer a half-written buffer.
+                if epoch > 0:
+                    self.check_error()
                 stream = self.torch.cuda.current_stream().cuda_stream
                 self.C.wait_flags(self._produced_ptr(self.rank, slot, 0), self.world,
                                   epoch + 1, int(self.flag_timeout_s * 1e9),

@@ -318,6 +318,31 @@ def test_backpressure_modes(tmp_path_factory, mode):
         dev.close(); cpu.close()
 
 
+@pytest.mark.parametrize("mode", ["stream", "host"])
+def test_stalled_consumer_is_reported_not_hung(tmp_path_factory, mode):
+    """Fault injection (the reference deadlocks on a dead trainer):
+    a trainer that never releases its epoch must surface as a TimeoutError
+    within flag_timeout_s - from the host poll, or from the error word a
+    device-side wait kernel leaves behind."""
+    files = _float_files(tmp_path_factory, 16, name="fi" + mode)
+    cols = [f"f{i}" for i in range(15)] + ["labels"]
+    cpu, dev = _engines(files, _f32_layout(cols), 1, backpressure=mode, flag_timeout_s=0.5)
+    try:
+        b0 = dev.start_epoch(0)
+        b1 = dev.start_epoch(1)
+        b0[0].wait(30); b1[0].wait(30)          # both slots full, nothing released
+        if mode == "host":
+            with pytest.raises(TimeoutError, match="did not release epoch 0"):
+                dev.start_epoch(2)
+        else:
+            dev.start_epoch(2)                   # enqueues the wait kernel; gives up after 0.5 s
+            torch.cuda.synchronize()
+            with pytest.raises(TimeoutError, match="device-side flag wait timed out"):
+                dev.check_error()
+    finally:
+        dev.close(); cpu.close()
+
+
 def _image_files(tmp_path_factory, n=3001, px=3 * 16 * 16):
     import pyarrow as pa
     import pyarrow.parquet as pq
