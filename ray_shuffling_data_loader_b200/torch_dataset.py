@@ -58,6 +58,9 @@ class TorchShufflingDataset(IterableDataset):
         packed_features (bool): yield ``(features[B, F], label)`` with one
             matrix instead of a list of ``(B, 1)`` views (needs a single
             feature dtype). Extension; default False = reference contract.
+        row_align (int): opt-in padding of the packed row pitch to a multiple
+            of this power of two (e.g. 128 = one L2 line); see
+            ``ops/layout.py::build_layout``.
         fp8_block_scale (bool): with ``feature_types`` all
             ``torch.float8_e4m3fn``, emit MX-style block-scaled fp8 (one UE8M0
             scale per 32 features, see ``ops/fp8.py``); the batch then yields
@@ -83,6 +86,7 @@ class TorchShufflingDataset(IterableDataset):
                  *,
                  packed_features: bool = False,
                  fp8_block_scale: bool = False,
+                 row_align: int = 0,
                  **dataset_options):
         super().__init__()
         spec = _normalize_torch_data_spec(feature_columns, feature_shapes,
@@ -92,7 +96,8 @@ class TorchShufflingDataset(IterableDataset):
         self._packed_features = packed_features
         self._fp8_block_scale = fp8_block_scale
         self._layout_fn = functools.partial(torch_layout, spec=spec,
-                                            fp8_block_scale=fp8_block_scale)
+                                            fp8_block_scale=fp8_block_scale,
+                                            row_align=row_align)
         self._ds = ShufflingDataset(
             filenames,
             num_epochs,
@@ -180,7 +185,7 @@ class TorchShufflingDataset(IterableDataset):
                                     self._packed_features)
 
 
-def torch_layout(schema, spec, fp8_block_scale: bool = False) -> L.RowLayout:
+def torch_layout(schema, spec, fp8_block_scale: bool = False, row_align: int = 0) -> L.RowLayout:
     """Row layout for a Torch data spec: features in the given order, then the
     label; each source column is cast to its requested dtype."""
     (feature_columns, feature_shapes, feature_types, label_column, label_shape,
@@ -194,7 +199,7 @@ def torch_layout(schema, spec, fp8_block_scale: bool = False) -> L.RowLayout:
                            f"{list(schema)}")
         src_code, width = schema[name]
         cols.append((name, src_code, L.code_from_torch(dtype), max(1, width)))
-    return L.build_layout(cols, fp8_block_scale=fp8_block_scale)
+    return L.build_layout(cols, fp8_block_scale=fp8_block_scale, row_align=row_align)
 
 
 def packed_to_tensors(packed: torch.Tensor, layout: L.RowLayout, spec,

@@ -97,3 +97,18 @@ def test_block_scaled_fp8():
     blockmax = np.repeat(np.abs(np.pad(x, ((0, 0), (0, 26)))).reshape(n, 3, 32).max(2), 32, 1)[:, :f]
     assert np.all(np.abs(deq - x) <= blockmax * 2.0 ** -4 + 1e-30)
     assert np.array_equal(L.unpack_field(packed, lay.field("labels")), cols["labels"])
+
+
+def test_row_align_pads_pitch_only():
+    import pytest
+    from ray_shuffling_data_loader_b200.ops import layout as L
+    cols = [(f"c{i}", L.DT_I64, L.DT_F32, 1) for i in range(21)]
+    base = L.build_layout(cols)
+    wide = L.build_layout(cols, row_align=128)
+    assert base.row_pitch == 96 and wide.row_pitch == 128
+    assert [f.offset for f in base.fields] == [f.offset for f in wide.fields]
+    data = {f"c{i}": np.arange(10, dtype=np.int64) * (i + 1) for i in range(21)}
+    a, b = L.pack_rows(data, base), L.pack_rows(data, wide)
+    assert np.array_equal(a[:, :84], b[:, :84]) and not b[:, 84:].any()
+    with pytest.raises(ValueError):
+        L.build_layout(cols, row_align=48)
