@@ -95,3 +95,37 @@ def test_native_pack_rows_all_casts_match_numpy_golden():
         assert np.array_equal(a, b, equal_nan=False) or np.array_equal(
             a.view(np.uint8), b.view(np.uint8)), (f.name, f.src_code, f.dst_code)
     assert np.array_equal(got, want)          # padding bytes are zero in both
+
+
+def test_perm_cuh_matches_numpy_property():
+    """Property test of the shared bijection (csrc/perm.cuh, compiled for the
+    host here and for sm_100a in the kernels) against ops/perm.py over random
+    table sizes - including > 2^32 rows, where both sides take their 64-bit
+    paths - seeds, epochs, trainer counts and source offsets."""
+    hyp = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+    pool = _C.HostPool(2)
+
+    @settings(max_examples=60, deadline=None)
+    @given(n=st.one_of(st.integers(1, 5000), st.integers(1 << 20, 1 << 22),
+                       st.integers((1 << 32) - 5, (1 << 32) + 5), st.integers(1 << 40, (1 << 40) + 99)),
+           seed=st.integers(0, 2**63 - 1), epoch=st.integers(0, 1000),
+           T=st.integers(1, 64), frac=st.floats(0, 1))
+    def check(n, seed, epoch, T, frac):
+        T = min(T, n)
+        cnt = min(n, 257)
+        off = int((n - cnt) * frac)
+        key = perm.make_key(n, seed, epoch)
+        plan = ShufflePlan(n, T, T, 10)
+        tr = np.empty(cnt, dtype=np.int32)
+        sl = np.empty(cnt, dtype=np.int64)
+        _C.host_perm_positions(pool, list(key.as_words()), n, T, off, cnt,
+                               tr.ctypes.data, sl.ctypes.data)
+        pos = perm.permute(np.arange(off, off + cnt, dtype=np.uint64), key)
+        assert pos.max() < n
+        t_ref, s_ref = plan.position_to_trainer(pos)
+        assert np.array_equal(tr, t_ref) and np.array_equal(sl, s_ref)
+        # and it really is a bijection on the sampled range
+        assert np.array_equal(perm.inverse(pos, key), np.arange(off, off + cnt, dtype=np.uint64))
+
+    check()
