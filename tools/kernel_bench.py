@@ -54,6 +54,8 @@ def main():
                     help="with --peer and --trainers 2: trainer 0 local, trainer 1 on the peer")
     ap.add_argument("--identity", action="store_true", help="identity permutation (sequential dst)")
     ap.add_argument("--ext", default=None, help="path to an alternative _C build")
+    ap.add_argument("--row-align", type=int, default=0,
+                    help="round the destination row pitch up to this power of two (0: layout default)")
     ap.add_argument("--sched", type=int, default=-1,
                     help="producer schedule: -1 auto, 0 loader warps, 1 cooperative")
     ap.add_argument("--tag", default="")
@@ -75,6 +77,8 @@ def main():
     payload = F * dsz
     scale_off = (payload + 15) // 16 * 16
     pitch = ((scale_off + (F + 31) // 32 if a.mode == 2 else payload) + 31) // 32 * 32
+    if a.row_align:
+        pitch = (pitch + a.row_align - 1) // a.row_align * a.row_align
     T = a.trainers
     per = -(-n // T)
     dst = torch.zeros((T, per, pitch), dtype=torch.uint8, device="cuda")
