@@ -130,6 +130,9 @@ class ShufflingDataset:
         if owner:
             # Owner process: build the engine, the queue and kick off shuffling.
             from ray_shuffling_data_loader_b200.runtime.engine import make_engine
+            # pandas batches are copies of the rows, so the host engine may reuse
+            # an epoch's buffer once this iterator has released it
+            engine_options.setdefault("recycle_buffers", output in (None, "pandas"))
             self._engine = make_engine(
                 filenames, num_trainers=num_trainers, num_reducers=num_reducers,
                 batch_size=batch_size, drop_last=drop_last, layout_fn=layout_fn,

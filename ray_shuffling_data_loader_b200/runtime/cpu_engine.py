@@ -78,7 +78,7 @@ class CpuShuffleEngine:
                  layout_fn, seed: int, rank: int = 0, world: int = 1,
                  stats_collector=None, num_threads: Optional[int] = None,
                  process_group=None, index: Optional[ingest.DatasetIndex] = None,
-                 native: Optional[bool] = None):
+                 native: Optional[bool] = None, recycle_buffers: bool = False):
         self.index = index or ingest.scan_files(filenames)
         self.C = _load_native() if native in (None, True) else None
         if native is True and self.C is None:
@@ -98,6 +98,12 @@ class CpuShuffleEngine:
         self._pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="cpu-shuffle")
         self._host_pool = self.C.HostPool(self.num_threads) if self.C is not None else None
         self._packed: Optional[np.ndarray] = None
+        # Released epoch buffers are reused (the host analogue of the device
+        # epoch ring) when the consumer only ever sees copies of the rows - the
+        # pandas output path; a fresh multi-GB buffer per epoch costs one page
+        # fault per 4 KB before the first row lands.
+        self._recycle = bool(recycle_buffers)
+        self._free: Dict[tuple, List[np.ndarray]] = {}
         self._lock = threading.Lock()
         self._ingest_reads: List[float] = []
         self._bytes_in_flight = 0
@@ -144,13 +150,34 @@ class CpuShuffleEngine:
         buffers = {}
         for t in self.local_trainers:
             rows = plan.trainer_rows(t)
-            data = np.empty((rows, layout.row_pitch), dtype=np.uint8)
-            buffers[t] = EpochBuffer(epoch, t, rows, layout, data, "cpu")
+            shape = (rows, layout.row_pitch)
+            data = None
+            if self._recycle:
+                with self._lock:
+                    pool = self._free.get(shape)
+                    data = pool.pop() if pool else None
+            if data is None:
+                data = np.empty(shape, dtype=np.uint8)
+            buffers[t] = EpochBuffer(epoch, t, rows, layout, data, "cpu",
+                                     release_fn=(self._make_recycler(data)
+                                                 if self._recycle else None))
+            # (a CPU buffer with a release_fn still waits on its ready event)
             self._bytes_in_flight += data.nbytes
         from ray_shuffling_data_loader_b200 import stats as stats_mod
         stats_mod.note_bytes_in_use(self.bytes_in_use())
         self._pool.submit(self._run_epoch, epoch, buffers)
         return buffers
+
+    def _make_recycler(self, data: np.ndarray):
+        def recycle():
+            if self._closed:
+                return
+            with self._lock:
+                pool = self._free.setdefault(data.shape, [])
+                if len(pool) < 4:                 # never hoard more than a few epochs
+                    pool.append(data)
+            self._bytes_in_flight -= data.nbytes
+        return recycle
 
     def _run_epoch(self, epoch: int, buffers: Dict[int, EpochBuffer]):
         try:
@@ -237,4 +264,5 @@ class CpuShuffleEngine:
             stats_mod.unregister_bytes_used_source(self._bytes_fn)
             self._pool.shutdown(wait=True)
             self._host_pool = None
+            self._free.clear()
             self._packed = None

@@ -51,6 +51,7 @@ def make_engine(filenames: Sequence[str], *, num_trainers: int, num_reducers: in
     plan_args = dict(num_trainers=num_trainers, num_reducers=num_reducers,
                      batch_size=batch_size, drop_last=drop_last)
     backend = resolve_backend(backend)
+    recycle = bool(options.pop("recycle_buffers", False))       # host engine only
     if backend == "cuda":
         from ray_shuffling_data_loader_b200.runtime.device_engine import DeviceShuffleEngine
         return DeviceShuffleEngine(filenames, plan_args, layout_fn, seed, rank=rank,
@@ -60,4 +61,5 @@ def make_engine(filenames: Sequence[str], *, num_trainers: int, num_reducers: in
     cpu_opts = {k: v for k, v in options.items()
                 if k in ("num_threads", "process_group", "index", "native")}
     return CpuShuffleEngine(filenames, plan_args, layout_fn, seed, rank=rank,
-                            world=world, stats_collector=stats_collector, **cpu_opts)
+                            world=world, stats_collector=stats_collector,
+                            recycle_buffers=recycle, **cpu_opts)

@@ -129,3 +129,30 @@ def test_perm_cuh_matches_numpy_property():
         assert np.array_equal(perm.inverse(pos, key), np.arange(off, off + cnt, dtype=np.uint64))
 
     check()
+
+
+def test_cpu_engine_recycles_released_buffers(small_dataset):
+    """pandas output: a released epoch buffer is reused by a later epoch (no
+    fresh multi-GB allocation per epoch) and the data stays exactly-once."""
+    from ray_shuffling_data_loader_b200 import ShufflingDataset
+    files, n = small_dataset
+    ds = ShufflingDataset(files, 5, 1, 1000, 0, num_reducers=2, backend="cpu", seed=4)
+    eng = ds._engine
+    assert eng._recycle
+    seen_ptrs = []
+    for epoch in range(5):
+        ds.set_epoch(epoch)
+        keys = []
+        for df in ds:
+            keys.append(df["key"].to_numpy())
+        assert np.array_equal(np.sort(np.concatenate(keys)), np.arange(n))
+        seen_ptrs.append(sum(len(v) for v in eng._free.values()))
+    assert max(seen_ptrs) >= 1                       # something came back to the pool
+    # torch output hands out views: never recycled
+    from ray_shuffling_data_loader_b200 import TorchShufflingDataset
+    tds = TorchShufflingDataset(files, 1, 1, 1000, 0, num_reducers=2, backend="cpu",
+                                feature_columns=["embeddings_name0"], label_column="labels")
+    assert not tds.dataset._engine._recycle
+    tds.set_epoch(0)
+    for _ in tds:
+        pass
