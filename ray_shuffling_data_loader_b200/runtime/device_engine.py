@@ -431,11 +431,20 @@ class DeviceShuffleEngine:
                 break
             n += 1
             off += dsz
+        # The kernel writes whole 16-byte groups. When another field starts inside
+        # the prefix's last, partly filled group (e.g. 5 x f32 then an int64 at
+        # byte 24), give the odd fields of that group to the generic kernel
+        # rather than the whole row (mode 2's blocks of 32 cannot be split).
+        per_group = 16 // dsz
+        if mode != 2 and n < len(fields) and n % per_group \
+                and fields[n].offset < _align(off, 16):
+            n -= n % per_group
+            off = n * dsz
         if mode == 4:
             self.fast_kinds = [_KINDS_8_TO_4[(f.src_code, f.dst_code)] for f in fields[:n]]
         if n < 4:
             return 0, [], -1       # not worth a TMA launch
-        fast_end = _align(off, 16)  # the kernel writes whole 16-byte groups
+        fast_end = _align(off, 16)
         rest = fields[n:]
         if rest:
             rest_lo = min(f.offset for f in rest)

@@ -205,6 +205,23 @@ def test_typed64_prefix_then_generic_tail(small_dataset):
         dev.close(); cpu.close()
 
 
+def test_prefix_trimmed_to_whole_16_byte_groups(small_dataset):
+    """5 x (int64 -> f32) followed by an int64 at byte 24: the TMA kernel takes
+    the 4 fields of the full 16-byte group, the generic kernel the rest."""
+    files, n = small_dataset
+
+    def fn(schema):
+        return L.build_layout([(f"embeddings_name{i}", L.DT_I64, L.DT_F32, 1) for i in range(5)]
+                              + [("key", L.DT_I64, L.DT_I64, 1), ("labels", L.DT_F64, L.DT_F32, 1)])
+    cpu, dev = _engines(files, fn, 2)
+    assert dev.fast_mode == 4 and len(dev.fast_field_idx) == 4 and dev.fast_write_end == 16
+    assert len(dev.generic_field_idx) == 3
+    try:
+        _compare_epochs(cpu, dev, epochs=(0, 1))
+    finally:
+        dev.close(); cpu.close()
+
+
 def test_generic_casts_match_golden(small_dataset):
     files, n = small_dataset
 

@@ -1,0 +1,114 @@
+"""The device engine's kernel planner (which scatter kernel writes which bytes
+of a packed row) is pure Python: exercise it without a GPU by building the
+engine object without running its constructor."""
+import numpy as np
+import pytest
+
+from ray_shuffling_data_loader_b200.ops import layout as L
+from ray_shuffling_data_loader_b200.runtime import device_engine as DE
+
+
+def _plan(layout, force_generic=False):
+    eng = object.__new__(DE.DeviceShuffleEngine)
+    eng.layout = layout
+    eng.src_fields = list(layout.fields)
+    eng.force_generic = force_generic
+    eng._plan_kernels()
+    return eng
+
+
+def _cover(eng):
+    """Byte ranges claimed by the three kernels; they must not overlap."""
+    ranges = []
+    if eng.fast_mode >= 0:
+        ranges.append((0, eng.fast_write_end))
+    for i in eng.wide_field_idx:
+        f = eng.src_fields[i]
+        ranges.append((f.offset, f.offset + f.dst_bytes))
+    for _, lo, hi in eng.generic_runs:
+        ranges.append((lo, hi))
+    ranges.sort()
+    for (a, b), (c, d) in zip(ranges, ranges[1:]):
+        assert b <= c, ranges
+    return ranges
+
+
+def test_f32_table_is_one_tma_launch_and_owns_the_padding():
+    lay = L.build_layout([(f"f{i}", L.DT_F32, L.DT_F32, 1) for i in range(17)])
+    eng = _plan(lay)
+    assert eng.fast_mode == 0 and len(eng.fast_field_idx) == 17
+    assert not eng.generic_runs and not eng.wide_field_idx
+    assert lay.row_pitch == 96 and eng.fast_write_end == 96      # zero-fills bytes 68..95
+
+
+@pytest.mark.parametrize("dst,mode", [(L.DT_BF16, 1), (L.DT_FP8, 2)])
+def test_f32_casts(dst, mode):
+    lay = L.build_layout([(f"f{i}", L.DT_F32, dst, 1) for i in range(64)],
+                         fp8_block_scale=(dst == L.DT_FP8))
+    eng = _plan(lay)
+    assert eng.fast_mode == mode
+    if mode == 2:
+        assert eng.fast_write_end == 64          # payload only: the scales follow
+    _cover(eng)
+
+
+def test_data_spec_native_and_torch_defaults():
+    from ray_shuffling_data_loader_b200.data_generation import DATA_SPEC
+    schema = {"key": (L.DT_I64, 1)}
+    schema.update({c: (L.code_from_numpy(dt), 1) for c, (_, _, dt) in DATA_SPEC.items()})
+    native = _plan(L.dataframe_layout(schema))
+    assert native.fast_mode == 3 and len(native.fast_field_idx) == 21
+    assert native.fast_write_end == native.layout.row_pitch == 192
+    feats = [c for c in schema if c != "key"]
+    torchy = _plan(L.build_layout([(c, schema[c][0], L.DT_F32, 1) for c in feats]))
+    assert torchy.fast_mode == 4
+    assert torchy.fast_kinds == [0] * 19 + [1]                  # int64 -> f32 ..., float64 -> f32
+    assert torchy.fast_write_end == torchy.layout.row_pitch == 96
+
+
+def test_mixed_prefix_tail_and_kinds():
+    cols = [("a", L.DT_I64, L.DT_F32, 1), ("b", L.DT_F64, L.DT_F32, 1),
+            ("c", L.DT_I64, L.DT_I32, 1), ("d", L.DT_I64, L.DT_F32, 1),
+            ("e", L.DT_I64, L.DT_F32, 1),
+            ("key", L.DT_I64, L.DT_I64, 1), ("flag", L.DT_BOOL, L.DT_U8, 1)]
+    eng = _plan(L.build_layout(cols))
+    # 5 x 4 B then an int64 at byte 24: the TMA kernel keeps the 4 fields of the
+    # full 16-byte group, field "e" joins the generic tail
+    assert eng.fast_mode == 4 and eng.fast_kinds == [0, 1, 2, 0]
+    assert eng.fast_write_end == 16
+    assert [eng.src_fields[i].name for i in eng.generic_field_idx] == ["e", "key", "flag"]
+    _cover(eng)
+    # a tail that starts on the group boundary leaves the prefix whole
+    cols8 = cols[:5] + [("f", L.DT_I64, L.DT_F32, 1), ("g", L.DT_I64, L.DT_F32, 1),
+                        ("h", L.DT_I64, L.DT_F32, 1)] + cols[5:]
+    eng8 = _plan(L.build_layout(cols8))
+    assert eng8.fast_mode == 4 and len(eng8.fast_field_idx) == 8 and eng8.fast_write_end == 32
+    _cover(eng8)
+
+
+def test_short_or_unsupported_prefixes_fall_back_to_generic():
+    three = _plan(L.build_layout([(f"f{i}", L.DT_F32, L.DT_F32, 1) for i in range(3)]))
+    assert three.fast_mode == -1 and len(three.generic_runs) == 1
+    assert three.generic_runs[0][1:] == (0, three.layout.row_pitch)
+    i16 = _plan(L.build_layout([(f"h{i}", L.DT_I16, L.DT_F32, 1) for i in range(8)]))
+    assert i16.fast_mode == -1
+    to_bf16 = _plan(L.build_layout([(f"x{i}", L.DT_I64, L.DT_BF16, 1) for i in range(8)]))
+    assert to_bf16.fast_mode == -1                              # no 8 -> 2 byte TMA mode
+    forced = _plan(L.build_layout([(f"f{i}", L.DT_F32, L.DT_F32, 1) for i in range(64)]),
+                   force_generic=True)
+    assert forced.fast_mode == -1
+
+
+def test_image_column_takes_the_wide_kernel():
+    lay = L.build_layout([("image", L.DT_F32, L.DT_BF16, 3 * 8 * 8), ("labels", L.DT_I64, L.DT_I64, 1),
+                          ("w", L.DT_F32, L.DT_F32, 1)])
+    eng = _plan(lay)
+    assert eng.wide_field_idx == [0] and eng.fast_mode == -1
+    assert [eng.src_fields[i].name for i in eng.generic_field_idx] == ["labels", "w"]
+    _cover(eng)
+
+
+def test_row_align_extends_the_zero_filled_tail():
+    lay = L.build_layout([(f"c{i}", L.DT_I64, L.DT_F32, 1) for i in range(21)], row_align=128)
+    eng = _plan(lay)
+    assert eng.fast_mode == 4 and eng.fast_write_end == 128
