@@ -112,3 +112,45 @@ def test_row_align_extends_the_zero_filled_tail():
     lay = L.build_layout([(f"c{i}", L.DT_I64, L.DT_F32, 1) for i in range(21)], row_align=128)
     eng = _plan(lay)
     assert eng.fast_mode == 4 and eng.fast_write_end == 128
+
+
+def test_planner_invariants_property():
+    """Random layouts: every field is written by exactly one kernel, no two
+    kernels claim the same byte, TMA fields sit inside the TMA byte range."""
+    pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+    casts = {L.DT_F32: [L.DT_F32, L.DT_BF16, L.DT_F16],
+             L.DT_I64: [L.DT_I64, L.DT_F32, L.DT_I32, L.DT_BF16],
+             L.DT_F64: [L.DT_F64, L.DT_F32], L.DT_I32: [L.DT_I32, L.DT_F32],
+             L.DT_U8: [L.DT_U8, L.DT_F32], L.DT_I16: [L.DT_I16]}
+    field = st.sampled_from(list(casts)).flatmap(
+        lambda src: st.tuples(st.just(src), st.sampled_from(casts[src]),
+                              st.sampled_from([1, 1, 1, 1, 1, 3, 16, 48])))
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.lists(field, min_size=1, max_size=40), st.sampled_from([0, 0, 64, 128]))
+    def check(spec, align):
+        cols = [(f"c{i}", s, d, w) for i, (s, d, w) in enumerate(spec)]
+        lay = L.build_layout(cols, row_align=align)
+        try:
+            eng = _plan(lay)
+        except ValueError as e:           # the documented refusal, never a wrong plan
+            assert "overlap" in str(e)
+            return
+        claimed = sorted(eng.fast_field_idx + eng.wide_field_idx + eng.generic_field_idx)
+        assert claimed == list(range(len(lay.fields)))
+        ranges = _cover(eng)
+        assert all(b <= lay.row_pitch for _, b in ranges)
+        for i in eng.fast_field_idx:
+            f = lay.fields[i]
+            assert f.offset + f.dst_bytes <= eng.fast_write_end
+        for idxs, lo, hi in eng.generic_runs:
+            for i in idxs:
+                f = lay.fields[i]
+                assert lo <= f.offset and f.offset + f.dst_bytes <= hi
+        if eng.fast_mode in (3, 4):
+            assert all(L.itemsize(lay.fields[i].src_code) == 8 for i in eng.fast_field_idx)
+        if eng.fast_mode == 4:
+            assert len(eng.fast_kinds) == len(eng.fast_field_idx)
+
+    check()
