@@ -110,6 +110,10 @@ class RowLayout:
     # dst_code == DT_FP8 are scaled per 32-element block by an UE8M0 exponent
     # stored at ``scale_offset + block_index``.
     scale_offset: int = -1
+    # User-facing column order as indices into ``fields`` (None: storage order).
+    # ``dataframe_layout`` may store columns in a kernel-friendly order while
+    # DataFrames / ``DeviceBatch.columns`` keep the file's order.
+    display_order: Optional[Tuple[int, ...]] = None
 
     def field(self, name: str) -> Field:
         for f in self.fields:
@@ -119,7 +123,14 @@ class RowLayout:
 
     @property
     def names(self) -> List[str]:
-        return [f.name for f in self.fields]
+        """Column names in user-facing order."""
+        return [f.name for f in self.display_fields]
+
+    @property
+    def display_fields(self) -> Tuple[Field, ...]:
+        if self.display_order is None:
+            return self.fields
+        return tuple(self.fields[i] for i in self.display_order)
 
     @property
     def payload_bytes(self) -> int:
@@ -193,11 +204,43 @@ def build_layout(columns: Sequence[Tuple[str, int, int, int]],
     return RowLayout(tuple(fields), max(16, pitch), scale_offset)
 
 
-def dataframe_layout(schema: Dict[str, Tuple[int, int]], row_align: int = 0) -> RowLayout:
-    """All columns, native dtypes, file order (``schema``: name -> (code, width)).
-    This is what plain ``ShufflingDataset`` shuffles (whole rows, like the
-    reference's DataFrames)."""
-    return build_layout([(n, c, c, w) for n, (c, w) in schema.items()], row_align=row_align)
+def dataframe_layout(schema: Dict[str, Tuple[int, int]], row_align: int = 0,
+                     optimize: bool = True) -> RowLayout:
+    """All columns, native dtypes (``schema``: name -> (code, width)). This is
+    what plain ``ShufflingDataset`` shuffles (whole rows, like the reference's
+    DataFrames).
+
+    *Storage* order: the TMA scatter kernel takes a dense prefix of same-class
+    scalar columns (identical 4-byte dtype, or any mix of 8-byte dtypes), so with
+    ``optimize`` the largest such class is stored first and everything else behind
+    it - an int64 ``key`` in front of 64 float32 features would otherwise push
+    the whole row onto the generic kernel. *User-facing* order (DataFrame columns,
+    ``DeviceBatch.columns``) stays the file's: see ``RowLayout.display_order``."""
+    items = list(schema.items())
+    order = list(range(len(items)))
+    if optimize and items:
+        classes: Dict[tuple, List[int]] = {}
+        for i, (_, (code, width)) in enumerate(items):
+            if width != 1:
+                continue
+            size = itemsize(code)
+            if size == 4:
+                classes.setdefault((4, code), []).append(i)
+            elif size == 8:
+                classes.setdefault((8,), []).append(i)
+        best = max(classes.values(), key=lambda idx: (len(idx) * itemsize(items[idx[0]][1][0]),
+                                                      -idx[0]), default=[])
+        if len(best) >= 4 and best != list(range(len(best))):
+            chosen = set(best)
+            order = best + [i for i in range(len(items)) if i not in chosen]
+    lay = build_layout([(items[i][0], items[i][1][0], items[i][1][0], items[i][1][1])
+                        for i in order], row_align=row_align)
+    if order == list(range(len(items))):
+        return lay
+    inverse = [0] * len(order)
+    for stored, original in enumerate(order):
+        inverse[original] = stored
+    return RowLayout(lay.fields, lay.row_pitch, lay.scale_offset, tuple(inverse))
 
 
 # ---------------------------------------------------------------------------

@@ -150,7 +150,7 @@ def packed_to_dataframe(packed: np.ndarray, layout: L.RowLayout):
     columns of ndarrays, like Parquet list columns read by pandas."""
     import pandas as pd
     cols = {}
-    for f in layout.fields:
+    for f in layout.display_fields:
         vals = L.unpack_field(packed, f)
         if f.width > 1:
             obj = np.empty(len(vals), dtype=object)

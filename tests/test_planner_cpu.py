@@ -154,3 +154,34 @@ def test_planner_invariants_property():
             assert len(eng.fast_kinds) == len(eng.fast_field_idx)
 
     check()
+
+
+def test_dataframe_layout_stores_the_tma_class_first():
+    """An int64 key in front of 64 float32 columns: stored behind them so the TMA
+    kernel takes the floats; user-facing column order stays the file's."""
+    schema = {"key": (L.DT_I64, 1)}
+    schema.update({f"f{i}": (L.DT_F32, 1) for i in range(63)})
+    schema["labels"] = (L.DT_F32, 1)
+    lay = L.dataframe_layout(schema)
+    assert [f.name for f in lay.fields[:3]] == ["f0", "f1", "f2"] and lay.fields[-1].name == "key"
+    assert lay.names == list(schema)                              # display order
+    assert lay.field("key").offset == 256 and lay.row_pitch == 288
+    eng = _plan(lay)
+    assert eng.fast_mode == 0 and len(eng.fast_field_idx) == 64
+    assert [eng.src_fields[i].name for i in eng.generic_field_idx] == ["key"]
+    _cover(eng)
+    # natural order already optimal (DATA_SPEC + key: all 8-byte) -> untouched
+    from ray_shuffling_data_loader_b200.data_generation import DATA_SPEC
+    s2 = {"key": (L.DT_I64, 1)}
+    s2.update({c: (L.code_from_numpy(dt), 1) for c, (_, _, dt) in DATA_SPEC.items()})
+    lay2 = L.dataframe_layout(s2)
+    assert lay2.display_order is None and [f.name for f in lay2.fields] == list(s2)
+    # opt-out
+    assert [f.name for f in L.dataframe_layout(schema, optimize=False).fields] == list(schema)
+    # round trip through pack / DataFrame keeps names and values
+    from ray_shuffling_data_loader_b200.runtime.chunks import packed_to_dataframe
+    data = {n: (np.arange(50, dtype=np.int64) if n == "key"
+                else np.full(50, i, dtype=np.float32)) for i, n in enumerate(schema)}
+    df = packed_to_dataframe(L.pack_rows(data, lay), lay)
+    assert list(df.columns) == list(schema)
+    assert np.array_equal(df["key"].to_numpy(), np.arange(50)) and df["f5"].iloc[0] == 6.0
