@@ -204,6 +204,46 @@ def build_layout(columns: Sequence[Tuple[str, int, int, int]],
     return RowLayout(tuple(fields), max(16, pitch), scale_offset)
 
 
+# (8-byte source, 4-byte destination) casts the TMA kernel converts in its epilogue
+# (csrc/shuffle_kernels.cu mode 4); runtime/device_engine.py maps them to kinds.
+TMA_CASTS_8_TO_4 = ((DT_I64, DT_F32), (DT_F64, DT_F32), (DT_I64, DT_I32))
+
+
+def tma_class(src_code: int, dst_code: int, width: int = 1):
+    """Key of the scatter_tma_kernel mode a scalar column can ride in (columns
+    with equal keys can share one launch as a dense run), or ``None``."""
+    if width != 1:
+        return None
+    ssz, dsz = itemsize(src_code), itemsize(dst_code)
+    if ssz == 4:
+        if dst_code == src_code or (src_code == DT_F32 and dst_code == DT_BF16):
+            return (4, src_code, dst_code)
+        return None
+    if ssz == 8:
+        if dsz == 8 and dst_code == src_code:
+            return (8, 8)
+        if dsz == 4 and (src_code, dst_code) in TMA_CASTS_8_TO_4:
+            return (8, 4)
+    return None
+
+
+def tma_friendly_order(columns: Sequence[Tuple[str, int, int, int]]) -> List[int]:
+    """Indices of ``columns`` ((name, src, dst, width)) with the largest
+    TMA-eligible class (by bytes, >= 4 columns) moved to the front; relative
+    order is otherwise preserved. Identity when nothing is gained."""
+    classes: Dict[tuple, List[int]] = {}
+    for i, (_, src, dst, width) in enumerate(columns):
+        key = tma_class(src, dst, width)
+        if key is not None:
+            classes.setdefault(key, []).append(i)
+    best = max(classes.values(),
+               key=lambda idx: (len(idx) * itemsize(columns[idx[0]][2]), -idx[0]), default=[])
+    if len(best) < 4 or best == list(range(len(best))):
+        return list(range(len(columns)))
+    chosen = set(best)
+    return best + [i for i in range(len(columns)) if i not in chosen]
+
+
 def dataframe_layout(schema: Dict[str, Tuple[int, int]], row_align: int = 0,
                      optimize: bool = True) -> RowLayout:
     """All columns, native dtypes (``schema``: name -> (code, width)). This is
@@ -219,20 +259,7 @@ def dataframe_layout(schema: Dict[str, Tuple[int, int]], row_align: int = 0,
     items = list(schema.items())
     order = list(range(len(items)))
     if optimize and items:
-        classes: Dict[tuple, List[int]] = {}
-        for i, (_, (code, width)) in enumerate(items):
-            if width != 1:
-                continue
-            size = itemsize(code)
-            if size == 4:
-                classes.setdefault((4, code), []).append(i)
-            elif size == 8:
-                classes.setdefault((8,), []).append(i)
-        best = max(classes.values(), key=lambda idx: (len(idx) * itemsize(items[idx[0]][1][0]),
-                                                      -idx[0]), default=[])
-        if len(best) >= 4 and best != list(range(len(best))):
-            chosen = set(best)
-            order = best + [i for i in range(len(items)) if i not in chosen]
+        order = tma_friendly_order([(n, c, c, w) for n, (c, w) in items])
     lay = build_layout([(items[i][0], items[i][1][0], items[i][1][0], items[i][1][1])
                         for i in order], row_align=row_align)
     if order == list(range(len(items))):

@@ -63,7 +63,7 @@ _FIELD_DTYPE = np.dtype([("src", "<u8"), ("src_code", "<u4"), ("dst_code", "<u4"
 
 
 # mode-4 conversion kinds (csrc/shuffle_kernels.cu): 8-byte source -> 4-byte field
-_KINDS_8_TO_4 = {(L.DT_I64, L.DT_F32): 0, (L.DT_F64, L.DT_F32): 1, (L.DT_I64, L.DT_I32): 2}
+_KINDS_8_TO_4 = {pair: kind for kind, pair in enumerate(L.TMA_CASTS_8_TO_4)}
 
 
 def _align(x: int, a: int = _ALIGN) -> int:

@@ -97,7 +97,8 @@ class TorchShufflingDataset(IterableDataset):
         self._fp8_block_scale = fp8_block_scale
         self._layout_fn = functools.partial(torch_layout, spec=spec,
                                             fp8_block_scale=fp8_block_scale,
-                                            row_align=row_align)
+                                            row_align=row_align,
+                                            reorder=not packed_features)
         self._ds = ShufflingDataset(
             filenames,
             num_epochs,
@@ -185,9 +186,14 @@ class TorchShufflingDataset(IterableDataset):
                                     self._packed_features)
 
 
-def torch_layout(schema, spec, fp8_block_scale: bool = False, row_align: int = 0) -> L.RowLayout:
+def torch_layout(schema, spec, fp8_block_scale: bool = False, row_align: int = 0,
+                 reorder: bool = False) -> L.RowLayout:
     """Row layout for a Torch data spec: features in the given order, then the
-    label; each source column is cast to its requested dtype."""
+    label; each source column is cast to its requested dtype. With ``reorder``
+    (tensors are looked up by column name, so storage order is free) the largest
+    class of columns the TMA scatter kernel can take in one launch is stored
+    first - e.g. an int64 id in front of 40 float features no longer sends the
+    whole row to the generic kernel."""
     (feature_columns, feature_shapes, feature_types, label_column, label_shape,
      label_type) = spec
     cols = []
@@ -199,6 +205,8 @@ def torch_layout(schema, spec, fp8_block_scale: bool = False, row_align: int = 0
                            f"{list(schema)}")
         src_code, width = schema[name]
         cols.append((name, src_code, L.code_from_torch(dtype), max(1, width)))
+    if reorder and not fp8_block_scale and len({c[0] for c in cols}) == len(cols):
+        cols = [cols[i] for i in L.tma_friendly_order(cols)]
     return L.build_layout(cols, fp8_block_scale=fp8_block_scale, row_align=row_align)
 
 

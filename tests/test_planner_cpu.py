@@ -185,3 +185,26 @@ def test_dataframe_layout_stores_the_tma_class_first():
     df = packed_to_dataframe(L.pack_rows(data, lay), lay)
     assert list(df.columns) == list(schema)
     assert np.array_equal(df["key"].to_numpy(), np.arange(50)) and df["f5"].iloc[0] == 6.0
+
+
+def test_torch_layout_reorders_storage_not_tensors(small_dataset):
+    """An int64 id (kept as int64) in front of float features: stored behind them;
+    the yielded feature list keeps the caller's order and values."""
+    torch = pytest.importorskip("torch")
+    from ray_shuffling_data_loader_b200 import TorchShufflingDataset
+    files, n = small_dataset
+    feats = ["key"] + [f"embeddings_name{i}" for i in range(6)]
+    types = [torch.int64] + [torch.float32] * 6
+    ds = TorchShufflingDataset(files, 1, 1, 1000, 0, num_reducers=2, backend="cpu", seed=2,
+                               feature_columns=feats, feature_types=types, label_column="labels")
+    lay = ds.dataset._engine.layout
+    assert lay.fields[0].name == "embeddings_name0" and lay.fields[-1].name == "key"
+    eng = _plan(lay)
+    assert eng.fast_mode == 4 and len(eng.fast_field_idx) == 7       # 6 features + label
+    ds.set_epoch(0)
+    keys = []
+    for features, label in ds:
+        assert len(features) == 7 and features[0].dtype == torch.int64
+        assert features[1].dtype == torch.float32 and features[1].shape[1] == 1
+        keys.append(features[0][:, 0].clone())
+    assert sorted(torch.cat(keys).tolist()) == list(range(n))
