@@ -73,10 +73,17 @@ def main(args):
         dist.barrier()
     _, files = bench.dataset_files(args, world)
 
-    steps = args.steps if args.ref_steps_cap is None else min(args.steps, args.ref_steps_cap)
-    warmup = args.warmup
+    # Same rule as our arm (bench.effective_counts): --steps/--warmup are minimums;
+    # warm up for >= max_concurrent_epochs whole epochs (those are shuffled at
+    # construction), then time a whole number of epochs. The reference's shuffle
+    # driver is a remote task with no handle to drain, so - unlike our arm - the
+    # region does not wait for the trailing in-flight epochs (this flatters it).
     batches_per_epoch = -(-args.rows_per_gpu // args.batch_size)
-    epochs = -(-(steps + warmup) // batches_per_epoch) + 1
+    window = max(1, args.max_concurrent_epochs)
+    warm_ep, timed_ep = bench.effective_counts(args.steps, args.warmup, batches_per_epoch,
+                                               window, min_timed_epochs=args.min_timed_epochs)
+    steps, warmup = timed_ep * batches_per_epoch, warm_ep * batches_per_epoch
+    epochs = warm_ep + timed_ep + window
 
     if rank == 0:
         ray.init()
@@ -85,18 +92,18 @@ def main(args):
     if rank != 0:
         ray.init(address="auto")
 
-    feature_columns = [f"f{i}" for i in range(args.cols - 1)]
+    feature_columns, label_column, _, _ = bench.schema_setup(args, torch)
     t_construct = time.perf_counter()
     if rank == 0:
         ds = TorchShufflingDataset(files, epochs, world, args.batch_size, rank,
-                                   num_reducers=world, max_concurrent_epochs=2,
-                                   feature_columns=feature_columns, label_column="labels")
+                                   num_reducers=world, max_concurrent_epochs=window,
+                                   feature_columns=feature_columns, label_column=label_column)
     if world > 1:
         dist.barrier()
     if rank != 0:
         ds = TorchShufflingDataset(files, epochs, world, args.batch_size, rank,
-                                   num_reducers=world, max_concurrent_epochs=2,
-                                   feature_columns=feature_columns, label_column="labels")
+                                   num_reducers=world, max_concurrent_epochs=window,
+                                   feature_columns=feature_columns, label_column=label_column)
 
     sampler = bench.ClockSampler(range(world)) if rank == 0 else None
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -164,12 +171,10 @@ def main(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "float32", "data": "synthetic", "impl": "reference",
             "substrate": substrate,
-            "config": {"model": f"TorchShufflingDataset {world} trainers x {world} reducers",
-                       "global_batch": args.batch_size * world,
-                       "rows": args.rows_per_gpu * world, "cols": args.cols,
-                       "batch_size": args.batch_size, "seq_len": None,
-                       "parallelism": f"dp{world}", "max_concurrent_epochs": 2,
-                       "l2_policy": "inputs larger than L2"},
+            "steps_requested": args.steps, "warmup_requested": args.warmup,
+            "epochs_timed": timed_ep, "epochs_warmup": warm_ep,
+            "batches_per_epoch": batches_per_epoch,
+            "config": bench.shape_config(args, world),
             "batches_per_sec": value / args.batch_size,
             "e2e": {"value": value, "unit": "rows/s",
                     "h2d_bytes_per_step": int(h2d_bytes / steps),

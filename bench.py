@@ -18,6 +18,16 @@ A *step* is one 250 000-row batch delivered to every trainer and fully consumed
               host memory*: every step pays the H2D copy of one batch worth of
               source rows (64 MB) and a D2H read of the step's result (8 B).
 
+``--steps`` / ``--warmup`` are minimums (see ``effective_counts``): the unit of
+work of a shuffling loader is an epoch, and the first ``max_concurrent_epochs``
+epochs are shuffled at construction, so both arms warm up for at least that many
+whole epochs and then time a whole number of epochs. In our arm the timed region
+opens and closes with a drained pipeline: exactly as many epochs are *shuffled*
+inside it (scatter kernels, and H2D copies in the e2e phase - both counted and
+reported) as are consumed. Every timed epoch is also checked for exactly-once
+delivery on all ranks (all-reduced fp64 sum of every delivered value == the same
+sum over the source table computed with plain torch).
+
 Timing rules followed: W >= 3 warm-up steps, inputs (3.2 GB/epoch/GPU) far
 larger than L2, CUDA events on the consumer stream bracketed by barrier +
 synchronize, max over ranks, nvidia-smi clock samples during the timed region.
@@ -83,15 +93,20 @@ def parse_args():
     p.add_argument("--exchange", choices=["p2p", "nccl"], default="p2p")
     p.add_argument("--feature-dtype", choices=["float32", "bfloat16", "fp8"], default="float32")
     p.add_argument("--peer-alloc", choices=["symm", "ipc"], default=None)
-    p.add_argument("--wait-mode", choices=["stream", "host"], default="stream",
+    p.add_argument("--wait-mode", choices=["stream", "host"], default=None,
                    help="how a trainer waits for an epoch's produced flags: a wait kernel on its "
-                        "own stream (no host round trip) or a host poll")
+                        "own stream (no host round trip; the engine default) or a host poll")
+    p.add_argument("--schema", choices=["f32", "dataspec"], default="f32",
+                   help="f32: --cols float32 columns (BASELINE config 2/4); dataspec: the "
+                        "reference's own DATA_SPEC table (key + 19 int64 + 1 float64, 168 B/row)")
+    p.add_argument("--row-align", type=int, default=0,
+                   help="pad the packed row pitch to a multiple of this (e.g. 128)")
+    p.add_argument("--min-timed-epochs", type=int, default=None,
+                   help="time at least this many whole epochs (default: ours 20, reference 1)")
     p.add_argument("--max-concurrent-epochs", type=int, default=2,
                    help="epoch window (BASELINE config 3 compares 1 vs 2)")
     p.add_argument("--skip-e2e", action="store_true")
     p.add_argument("--keep-data", action="store_true")
-    p.add_argument("--ref-steps-cap", type=int, default=None,
-                   help="reference arm: cap on timed steps (it is slow)")
     return p.parse_args()
 
 
@@ -101,7 +116,8 @@ def parse_args():
 
 def dataset_files(args, world):
     n_files = FILES_PER_GPU * world
-    d = os.path.join(args.data_dir, f"r{args.rows_per_gpu}_c{args.cols}_w{world}")
+    tag = f"c{args.cols}" if args.schema == "f32" else args.schema
+    d = os.path.join(args.data_dir, f"r{args.rows_per_gpu}_{tag}_w{world}")
     return d, [os.path.join(d, f"input_data_{i}.parquet.snappy") for i in range(n_files)]
 
 
@@ -113,7 +129,7 @@ def generate_my_share(args, rank, world):
     from ray_shuffling_data_loader_b200.data_generation import float_spec, generate_file
     d, files = dataset_files(args, world)
     os.makedirs(d, exist_ok=True)
-    spec = float_spec(args.cols, np.float32)
+    spec = float_spec(args.cols, np.float32) if args.schema == "f32" else None   # None: DATA_SPEC
     rows_per_file = args.rows_per_gpu // FILES_PER_GPU
     mine = range(rank * FILES_PER_GPU, (rank + 1) * FILES_PER_GPU)
     todo = [i for i in mine if not os.path.exists(files[i] + ".ok")]
@@ -123,7 +139,7 @@ def generate_my_share(args, rank, world):
                                 if i % FILES_PER_GPU == FILES_PER_GPU - 1 else 0)
         start = (i // FILES_PER_GPU) * args.rows_per_gpu + (i % FILES_PER_GPU) * rows_per_file
         generate_file(i, start, rows, ROW_GROUPS_PER_FILE, d, spec,
-                      np.random.SeedSequence([1234, i]), include_key=False)
+                      np.random.SeedSequence([1234, i]), include_key=args.schema != "f32")
         open(files[i] + ".ok", "w").close()
     if todo:
         with ThreadPoolExecutor(max_workers=len(todo)) as ex:
@@ -191,91 +207,167 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------
+# step / epoch accounting shared by both arms
+# ---------------------------------------------------------------------------
+
+def effective_counts(steps, warmup, batches_per_epoch, window, min_timed_epochs=1):
+    """``--steps`` / ``--warmup`` are *minimums*. The loader's unit of work is an
+    epoch (one shuffle of the table feeds ``batches_per_epoch`` steps) and the first
+    ``window`` epochs are shuffled at construction, so a clock around fewer steps
+    than that would time a consumer loop on pre-shuffled data. Both arms therefore
+    warm up for >= ``window`` whole epochs and time a whole number of epochs.
+    -> (warm_epochs, timed_epochs)"""
+    warm = max(window, -(-max(0, warmup) // batches_per_epoch))
+    timed = max(min_timed_epochs, -(-max(1, steps) // batches_per_epoch))
+    return warm, timed
+
+
+# ---------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------
 
-def run_phase(ds, engine, torch, dist, world, steps, warmup, batch_size, d2h_each_step):
-    """Consume ``warmup`` then ``steps`` batches. The clock starts BEFORE the first
-    timed batch is fetched, so waiting for that batch's epoch to be shuffled is
-    inside the timed region (no pre-shuffled epoch is consumed for free).
-    Returns (max-over-ranks device ms, wall s, launches in the region, checksum)."""
+def run_phase(ds, engine, torch, dist, world, warm_epochs, timed_epochs, d2h_each_step):
+    """Consume ``warm_epochs`` then ``timed_epochs`` whole epochs through the
+    public iterator.
+
+    Timed region (barrier + synchronize on both sides): it opens with a drained
+    pipeline - the ``window`` epochs in flight are completely shuffled - and it
+    closes only after the shuffles of the ``window`` epochs *following* the last
+    consumed one have landed on this rank. So exactly ``timed_epochs`` epochs are
+    consumed AND exactly ``timed_epochs`` epochs are shuffled (scatter kernels,
+    H2D copies in host mode) inside it; nothing is consumed for free.
+
+    Returns a dict: device ms (max over ranks), wall s, launch / byte counters of
+    the region and the per-epoch fp64 sums of everything that was consumed."""
     row_pitch = engine.layout.row_pitch
+    window = engine.window
     dev = torch.device("cuda", torch.cuda.current_device())
-    acc = torch.zeros(1, dtype=torch.float64, device=dev)
+    n_ep = warm_epochs + timed_epochs
+    sums = torch.zeros(n_ep, dtype=torch.float64, device=dev)
     host_acc = torch.zeros(1, dtype=torch.float64).pin_memory()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    state = {"it": None, "epoch": 0}
-
-    def next_batch():
-        while True:
-            if state["it"] is None:
-                ds.set_epoch(state["epoch"])
-                state["it"] = iter(ds)
-            try:
-                return next(state["it"])       # the public API: (features, label)
-            except StopIteration:
-                state["it"] = None
-                state["epoch"] += 1
-
     checksum = [0.0]
+    steps_done = [0]
 
-    def step():
-        features, label = next_batch()
-        # consume: every byte of the batch (features + label share one packed row;
-        # the feature view starts at the batch's first byte) is read by our kernel
-        base = features[0] if isinstance(features, tuple) else features
-        engine.batch_sum_all(base, acc, nbytes=base.shape[0] * row_pitch)
-        if d2h_each_step:
-            host_acc.copy_(acc, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            checksum[0] = float(host_acc[0])
+    def consume_epoch(epoch):
+        acc = sums[epoch:epoch + 1]
+        ds.set_epoch(epoch)
+        for features, label in ds:                # the public API: (features, label)
+            # consume: every byte of the batch (features + label share one packed
+            # row; the feature view starts at the batch's first byte) is read by
+            # our sink kernel and reduced in fp64
+            base = features[0] if isinstance(features, tuple) else features
+            engine.batch_sum_all(base, acc, nbytes=base.shape[0] * row_pitch)
+            if d2h_each_step:
+                host_acc.copy_(acc, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                checksum[0] = float(host_acc[0])
+            steps_done[0] += 1
 
-    for _ in range(warmup):
-        step()
+    for e in range(warm_epochs):
+        consume_epoch(e)
+    warm_steps = steps_done[0]
+    if not engine.wait_epochs_started(warm_epochs + window, 120.0):
+        raise RuntimeError("shuffle driver did not start the in-flight epochs")
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    launches0 = engine.launches
+    c0 = (engine.launches, engine.scatter_launches, engine.h2d_bytes_enqueued)
     wall0 = time.perf_counter()
     ev0.record()
-    for _ in range(steps):
-        step()
+    for e in range(warm_epochs, n_ep):
+        consume_epoch(e)
+    # close the books: the next ``window`` epochs must be shuffled inside the region
+    if not engine.wait_epochs_started(n_ep + window, 120.0):
+        raise RuntimeError("shuffle driver did not start the trailing epochs")
+    for e in range(n_ep, n_ep + window):
+        engine.enqueue_wait_produced(e)
     ev1.record()
     torch.cuda.synchronize()
     wall = time.perf_counter() - wall0
+    c1 = (engine.launches, engine.scatter_launches, engine.h2d_bytes_enqueued)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    launches = engine.launches - launches0
+    engine.check_error()
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
     wall_t = torch.tensor([wall], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(wall_t, op=dist.ReduceOp.MAX)
-    if not d2h_each_step:
-        checksum[0] = float(acc.item())
-    return float(ms.item()), float(wall_t.item()), launches, checksum[0]
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    kernel_ms = [engine.epoch_kernel_ms(e) for e in range(warm_epochs + window, n_ep + window)]
+    kernel_ms = [k for k in kernel_ms if k]
+    return {"ms": float(ms.item()), "wall": float(wall_t.item()),
+            "steps": steps_done[0] - warm_steps, "warm_steps": warm_steps,
+            "launches": c1[0] - c0[0], "scatter_launches": c1[1] - c0[1],
+            "h2d_bytes": c1[2] - c0[2], "epoch_sums": sums.cpu().tolist(),
+            "kernel_ms": kernel_ms, "checksum": checksum[0] if d2h_each_step else None}
+
+
+def expected_table_sum(engine, torch, dist, world):
+    """Ground truth for the exactly-once check, computed with plain torch from the
+    HBM-resident *source* columns (never touched by our kernels): the fp64 sum of
+    every value as the loader is asked to deliver it (fp32)."""
+    total = torch.zeros(1, dtype=torch.float64, device=torch.device("cuda", engine.device_index))
+    for f, col in engine.source_column_tensors():
+        total += col.to(torch.float32).sum(dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(total, op=dist.ReduceOp.SUM)
+    return float(total.item())
+
+
+def exactly_once(epoch_sums, expected, rel_tol=1e-9):
+    """Every epoch's all-reduced sum over every delivered value must equal the
+    table's. (A lost, duplicated or torn row changes the sum; the random fp32
+    payload makes an accidental match impossible in practice.)"""
+    worst = max((abs(s - expected) / max(1.0, abs(expected)) for s in epoch_sums), default=0.0)
+    return {"ok": bool(worst <= rel_tol), "epochs_checked": len(epoch_sums),
+            "expected_sum": expected, "max_rel_err": worst, "rel_tol": rel_tol}
+
+
+def schema_setup(args, torch):
+    """(feature columns, label column, feature dtype, source bytes per row)."""
+    dt = {"float32": torch.float32, "bfloat16": torch.bfloat16,
+          "fp8": getattr(torch, "float8_e4m3fn", None)}[args.feature_dtype]
+    if args.schema == "dataspec":
+        from ray_shuffling_data_loader_b200.data_generation import DATA_SPEC
+        names = ["key"] + list(DATA_SPEC.keys())
+        return names[:-1], names[-1], dt, 8 * len(names)
+    return [f"f{i}" for i in range(args.cols - 1)], "labels", dt, 4 * args.cols
 
 
 def make_dataset(args, files, rank, world, epochs, resident, torch, seed=20260921):
     """The flagship public API, exactly as a user would call it."""
     from ray_shuffling_data_loader_b200 import TorchShufflingDataset
-    feature_columns = [f"f{i}" for i in range(args.cols - 1)]
-    dt = {"float32": torch.float32, "bfloat16": torch.bfloat16,
-          "fp8": getattr(torch, "float8_e4m3fn", None)}[args.feature_dtype]
-    opts = dict(resident=resident, exchange=args.exchange, wait_mode=args.wait_mode)
+    feature_columns, label_column, dt, _ = schema_setup(args, torch)
+    opts = dict(resident=resident, exchange=args.exchange)
+    if args.wait_mode:
+        opts["wait_mode"] = args.wait_mode
     if args.peer_alloc:
         opts["peer_alloc"] = args.peer_alloc
+    if args.row_align:
+        opts["row_align"] = args.row_align
     if resident == "host":
         opts["stream_chunk_rows"] = args.batch_size
     fp8 = args.feature_dtype == "fp8"
     return TorchShufflingDataset(
         files, epochs, world, args.batch_size, rank, num_reducers=world,
         max_concurrent_epochs=args.max_concurrent_epochs, feature_columns=feature_columns,
-        feature_types=[dt] * len(feature_columns), label_column="labels",
+        feature_types=[dt] * len(feature_columns), label_column=label_column,
         label_type=dt if not fp8 else torch.float32, packed_features=True,
         fp8_block_scale=fp8, seed=seed, backend="cuda", queue_name=f"bench-{resident}", **opts)
+
+
+def shape_config(args, world):
+    """The benchmark *shape*: identical keys and values in both arms."""
+    return {"model": f"TorchShufflingDataset {world} trainers x {world} reducers",
+            "global_batch": args.batch_size * world,
+            "rows": args.rows_per_gpu * world, "cols": args.cols if args.schema == "f32" else 21,
+            "schema": args.schema, "batch_size": args.batch_size, "seq_len": None,
+            "parallelism": f"dp{world}", "max_concurrent_epochs": args.max_concurrent_epochs,
+            "l2_policy": "inputs larger than L2 (every epoch streams the whole per-GPU table)"}
 
 
 def run_ours(args):
@@ -289,47 +381,65 @@ def run_ours(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}; launch with torchrun")
     torch.cuda.set_device(ctx.local_rank if world > 1 else 0)
     t_gen = time.perf_counter()
-    files_mine = generate_my_share(args, rank, world)
+    generate_my_share(args, rank, world)
     if world > 1:
         dist.barrier()
     gen_s = time.perf_counter() - t_gen
     _, files = dataset_files(args, world)
     batches_per_epoch = -(-args.rows_per_gpu // args.batch_size)
-    total_steps = args.steps + args.warmup
-    epochs = -(-total_steps // batches_per_epoch) + 1
+    window = max(1, args.max_concurrent_epochs)
+    warm_ep, timed_ep = effective_counts(args.steps, args.warmup, batches_per_epoch, window,
+                                         min_timed_epochs=args.min_timed_epochs)
+    epochs = warm_ep + timed_ep + window
     sampler = ClockSampler(range(world)) if rank == 0 else None
+    _, _, _, src_row_bytes = schema_setup(args, torch)
 
     # ---- device-timed, HBM-resident -----------------------------------------
-    t0 = time.perf_counter()
+    t_first = time.perf_counter()
     ds = make_dataset(args, files, rank, world, epochs, "hbm", torch)
     engine = ds.dataset.engine
     if sampler:
         sampler.start()
-    ms, wall, launches, chk = run_phase(ds, engine, torch, dist, world, args.steps, args.warmup,
-                                        args.batch_size, d2h_each_step=False)
+    res = run_phase(ds, engine, torch, dist, world, warm_ep, timed_ep, d2h_each_step=False)
     clocks = sampler.stop() if sampler else None
     ingest_s = getattr(engine, "ingest_seconds", None)
-    kernel_ms = [engine.epoch_kernel_ms(e) for e in range(epochs) if engine.epoch_kernel_ms(e)]
+    check_sum = args.feature_dtype == "float32"
+    expected = expected_table_sum(engine, torch, dist, world) if check_sum else None
+    once = exactly_once(res["epoch_sums"], expected) if check_sum else None
     fast_mode = engine.fast_mode
     row_pitch = engine.layout.row_pitch
+    launches_per_epoch = None
+    if timed_ep:
+        launches_per_epoch = res["scatter_launches"] / timed_ep
+    engine_opts = {"exchange": args.exchange, "wait_mode": engine.wait_mode,
+                   "backpressure": engine.backpressure, "peer_alloc": engine.peer_alloc,
+                   "tmap_mode": engine.tmap_mode, "sched": engine.sched,
+                   "row_bytes": row_pitch, "row_align": args.row_align,
+                   "fast_mode": fast_mode}
     ds.dataset.close()
-    rows = args.steps * args.batch_size * world
-    value = rows / (ms / 1e3)
+    steps = res["steps"]
+    rows = timed_ep * args.rows_per_gpu * world       # rows delivered inside the region
+    value = rows / (res["ms"] / 1e3)
 
     # ---- end to end: pinned host table, H2D every step, D2H every step ---------
     e2e = None
     if not args.skip_e2e:
         ds2 = make_dataset(args, files, rank, world, epochs, "host", torch)
         eng2 = ds2.dataset.engine
-        ms2, wall2, launches2, chk2 = run_phase(ds2, eng2, torch, dist, world, args.steps,
-                                                args.warmup, args.batch_size, d2h_each_step=True)
-        h2d_epoch = eng2.h2d_bytes_per_epoch()
+        res2 = run_phase(ds2, eng2, torch, dist, world, warm_ep, timed_ep, d2h_each_step=True)
+        once2 = exactly_once(res2["epoch_sums"], expected) if check_sum else None
         ds2.dataset.close()
-        e2e = {"value": rows / wall2, "unit": "rows/s",
-               "h2d_bytes_per_step": int(h2d_epoch / batches_per_epoch),
-               "d2h_bytes_per_step": 8, "ms_per_step": wall2 * 1e3 / args.steps,
-               "device_ms_per_step": ms2 / args.steps, "gpu_launches": launches2,
-               "batches_per_sec": rows / wall2 / args.batch_size}
+        e2e = {"value": rows / res2["wall"], "unit": "rows/s",
+               # counted from the cudaMemcpyAsync calls enqueued inside the region
+               "h2d_bytes_per_step": int(res2["h2d_bytes"] / max(1, res2["steps"])),
+               "d2h_bytes_per_step": 8, "ms_per_step": res2["wall"] * 1e3 / res2["steps"],
+               "device_ms_per_step": res2["ms"] / res2["steps"], "steps": res2["steps"],
+               "gpu_launches": res2["launches"],
+               "scatter_launches_in_region": res2["scatter_launches"],
+               "h2d_bytes_in_region": res2["h2d_bytes"],
+               "h2d_gbps_per_gpu": res2["h2d_bytes"] / res2["wall"] / 1e9,
+               "batches_per_sec": rows / res2["wall"] / args.batch_size,
+               "exactly_once": once2}
     if rank == 0:
         peaks = {}
         try:
@@ -338,37 +448,47 @@ def run_ours(args):
         except Exception:
             pass
         # bytes the shuffle moves per epoch per GPU: read source once + write rows once
-        epoch_bytes = args.rows_per_gpu * (args.cols * 4 + row_pitch)
-        best_kernel_ms = min(kernel_ms) if kernel_ms else None
+        epoch_bytes = args.rows_per_gpu * (src_row_bytes + row_pitch)
+        kms = sorted(res["kernel_ms"])
+        kernel_ms = kms[len(kms) // 2] if kms else None         # median over the timed epochs
+        egress = (args.rows_per_gpu * row_pitch * (world - 1) / world / (kernel_ms / 1e3) / 1e9
+                  if kernel_ms and world > 1 else None)
         out = {
             "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "steps": steps, "warmup": res["warm_steps"],
+            "steps_requested": args.steps, "warmup_requested": args.warmup,
+            "epochs_timed": timed_ep, "epochs_warmup": warm_ep,
+            "batches_per_epoch": batches_per_epoch,
+            "ms_per_step": res["ms"] / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.feature_dtype, "data": "synthetic",
             "impl": "ours",
-            "config": {"model": f"TorchShufflingDataset {world} trainers x {world} reducers",
-                       "global_batch": args.batch_size * world,
-                       "rows": args.rows_per_gpu * world, "cols": args.cols,
-                       "row_bytes": row_pitch, "batch_size": args.batch_size,
-                       "seq_len": None, "parallelism": f"dp{world}",
-                       "max_concurrent_epochs": args.max_concurrent_epochs, "exchange": args.exchange,
-                       "wait_mode": args.wait_mode,
-                       "l2_policy": "inputs larger than L2 (3.2 GB/epoch/GPU)"},
+            "config": shape_config(args, world),
+            "engine": engine_opts,
             "batches_per_sec": value / args.batch_size,
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-            "wall_ms_per_step": wall * 1e3 / args.steps,
-            "shuffle_kernel_ms_per_epoch": best_kernel_ms,
-            "shuffle_kernel_gbps": (epoch_bytes / (best_kernel_ms / 1e3) / 1e9
-                                    if best_kernel_ms else None),
+            "e2e": e2e, "gpu_launches": res["launches"], "clocks": clocks,
+            "scatter_launches_in_region": res["scatter_launches"],
+            "scatter_launches_per_epoch": launches_per_epoch,
+            "wall_ms_per_step": res["wall"] * 1e3 / steps,
+            "ms_per_epoch": res["ms"] / timed_ep,
+            "shuffle_kernel_ms_per_epoch": kernel_ms,
+            "shuffle_kernel_ms_min_max": [kms[0], kms[-1]] if kms else None,
+            "shuffle_kernel_gbps": (epoch_bytes / (kernel_ms / 1e3) / 1e9 if kernel_ms else None),
             "hbm_roofline_frac_of_measured": (
-                epoch_bytes / (best_kernel_ms / 1e3) / 1e9 / peaks["hbm_gbs"]
-                if best_kernel_ms and peaks.get("hbm_gbs") else None),
-            "nvlink_egress_gbps_per_gpu": (
-                args.rows_per_gpu * row_pitch * (world - 1) / world / (best_kernel_ms / 1e3) / 1e9
-                if best_kernel_ms and world > 1 else None),
-            "ingest_seconds": ingest_s, "datagen_seconds": gen_s, "fast_mode": fast_mode,
-            "checksum": chk,
+                epoch_bytes / (kernel_ms / 1e3) / 1e9 / peaks["hbm_gbs"]
+                if kernel_ms and peaks.get("hbm_gbs") else None),
+            "nvlink_egress_gbps_per_gpu": egress,
+            "nvlink_frac_of_900": egress / 900.0 if egress else None,
+            "nvlink_frac_of_measured_peer_copy_774": egress / 774.0 if egress else None,
+            "exactly_once": once,
+            "ingest_seconds": ingest_s,
+            "cold_rows_per_sec": (args.rows_per_gpu * world / ingest_s if ingest_s else None),
+            "datagen_seconds": gen_s,
         }
+        if once is not None and not once["ok"]:
+            out["invalid"] = "exactly-once check failed"
+        if res["scatter_launches"] < timed_ep:
+            out["invalid"] = "no shuffle kernel launched inside the timed region"
         emit_json(out)
     if world > 1:
         dist.barrier()
@@ -391,6 +511,8 @@ if __name__ == "__main__":
     a = parse_args()
     if a.warmup < 3:
         a.warmup = 3
+    if a.min_timed_epochs is None:
+        a.min_timed_epochs = 20 if a.impl == "ours" else 1
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -271,16 +271,70 @@ _RPC_METHODS = {
 }
 
 
+def _queue_root() -> str:
+    """Private per-user directory holding the queue sockets and the RPC secret.
+
+    The RPC payloads are pickles, so whoever can serve (or talk to) the socket
+    can run code in the peer. The directory therefore must belong to this user
+    and be closed to everybody else: it is created 0700 under
+    ``$XDG_RUNTIME_DIR`` (else the temp dir) and an existing directory with
+    another owner or group/other permission bits is refused rather than trusted.
+    ``RSDL_B200_QUEUE_DIR`` overrides the location (same checks apply)."""
+    root = os.environ.get("RSDL_B200_QUEUE_DIR")
+    if not root:
+        base = os.environ.get("XDG_RUNTIME_DIR")
+        if not (base and os.path.isdir(base) and os.access(base, os.W_OK)):
+            base = tempfile.gettempdir()
+        root = os.path.join(base, f"rsdl_b200_{os.getuid()}")
+    try:
+        os.mkdir(root, 0o700)
+    except FileExistsError:
+        pass
+    except FileNotFoundError:
+        os.makedirs(root, mode=0o700, exist_ok=True)
+    st = os.stat(root)
+    if st.st_uid != os.getuid():
+        raise PermissionError(f"queue directory {root} is owned by uid {st.st_uid}, not by this "
+                              "user; refusing to use it (set RSDL_B200_QUEUE_DIR)")
+    if st.st_mode & 0o077:
+        os.chmod(root, 0o700)           # ours but too open (e.g. a mkdtemp'd test dir)
+    return root
+
+
 def _socket_path(name: str) -> str:
-    root = os.environ.get("RSDL_B200_QUEUE_DIR") or os.path.join(
-        tempfile.gettempdir(), f"rsdl_b200_{os.getuid()}")
-    os.makedirs(root, exist_ok=True)
     digest = hashlib.sha1(name.encode()).hexdigest()[:16]
-    return os.path.join(root, f"q_{digest}.sock")
+    return os.path.join(_queue_root(), f"q_{digest}.sock")
 
 
 def _authkey(name: str) -> bytes:
-    return hashlib.sha256(("rsdl-b200:" + name).encode()).digest()
+    """HMAC key of the connection handshake: a random secret kept in a 0600 file
+    inside the private directory (created on first use), mixed with the queue
+    name. Knowing the queue name is not enough to talk to the actor."""
+    path = os.path.join(_queue_root(), "secret")
+    for _ in range(50):
+        try:
+            with open(path, "rb") as f:
+                secret = f.read()
+            if len(secret) == 32:
+                break
+        except FileNotFoundError:
+            pass
+        try:
+            fd = os.open(path + f".{os.getpid()}", os.O_WRONLY | os.O_CREAT | os.O_EXCL, 0o600)
+        except FileExistsError:
+            time.sleep(0.01)
+            continue
+        with os.fdopen(fd, "wb") as f:
+            f.write(os.urandom(32))
+        try:
+            os.link(path + f".{os.getpid()}", path)     # atomic: first writer wins
+        except FileExistsError:
+            pass
+        finally:
+            os.unlink(path + f".{os.getpid()}")
+    else:
+        raise RuntimeError(f"could not read or create the queue secret {path}")
+    return hashlib.sha256(secret + b"rsdl-b200:" + name.encode()).digest()
 
 
 class _ActorHost:

@@ -65,8 +65,11 @@ PermKeyDev make_key(const std::vector<uint64_t>& w) {
   return k;
 }
 
-PlanDev make_plan(uint64_t num_rows, uint32_t num_trainers) {
+PlanDev make_plan(uint64_t num_rows, uint32_t num_trainers, uint64_t slot_lo = 0,
+          uint64_t slot_hi = ~0ull) {
   PlanDev p;
+  p.slot_lo = slot_lo;
+  p.slot_hi = slot_hi;
   p.q = num_rows / num_trainers;
   p.rem = static_cast<uint32_t>(num_rows % num_trainers);
   p.big = static_cast<unsigned long long>(p.rem) * (p.q + 1);
@@ -550,7 +553,8 @@ PYBIND11_MODULE(_C, m) {
            uintptr_t cols, uint32_t num_cols, uint64_t n_local, uint64_t global_offset,
            uint32_t row_pitch, uint32_t scale_offset, const std::vector<uintptr_t>& dst, int mode,
            int grid, uintptr_t stream, uintptr_t col_base, uint64_t col_stride,
-           uint64_t rows_alloc, int tmap_mode, uintptr_t kinds, uint32_t write_end, int sched) {
+           uint64_t rows_alloc, int tmap_mode, uintptr_t kinds, uint32_t write_end, int sched,
+           uint64_t slot_lo, uint64_t slot_hi) {
           FastParams p;
           std::memset(&p.tmap, 0, sizeof(p.tmap));
           p.use_tmap = 0;
@@ -564,7 +568,7 @@ PYBIND11_MODULE(_C, m) {
             p.use_tmap = dense ? 2 : 1;
           }
           p.key = make_key(key);
-          p.plan = make_plan(num_rows, num_trainers);
+          p.plan = make_plan(num_rows, num_trainers, slot_lo, slot_hi);
           p.cols = as_ptr<const uint8_t* const>(cols);
           p.kinds = as_ptr<const uint8_t>(kinds);
           p.num_cols = num_cols;
@@ -590,17 +594,19 @@ PYBIND11_MODULE(_C, m) {
         py::arg("scale_offset"), py::arg("dst"), py::arg("mode"), py::arg("grid"),
         py::arg("stream"), py::arg("col_base") = 0, py::arg("col_stride") = 0,
         py::arg("rows_alloc") = 0, py::arg("tmap_mode") = 2, py::arg("kinds") = 0,
-        py::arg("write_end") = 0, py::arg("sched") = -1);
+        py::arg("write_end") = 0, py::arg("sched") = -1, py::arg("slot_lo") = 0,
+        py::arg("slot_hi") = ~0ull);
   m.def("fast_src_itemsize", &rsdl::fast_src_itemsize);
   m.def("fast_ctas_per_sm", &rsdl::fast_ctas_per_sm);
   m.def("scatter_generic",
         [](const std::vector<uint64_t>& key, uint64_t num_rows, uint32_t num_trainers,
            uintptr_t fields, uint32_t num_fields, uint64_t n_local, uint64_t global_offset,
            uint32_t row_pitch, uint32_t write_lo, uint32_t write_hi,
-           const std::vector<uintptr_t>& dst, int grid, uintptr_t stream) {
+           const std::vector<uintptr_t>& dst, int grid, uintptr_t stream, uint64_t slot_lo,
+           uint64_t slot_hi) {
           GenericParams p;
           p.key = make_key(key);
-          p.plan = make_plan(num_rows, num_trainers);
+          p.plan = make_plan(num_rows, num_trainers, slot_lo, slot_hi);
           p.fields = as_ptr<const FieldDev>(fields);
           p.num_fields = num_fields;
           p.rows_per_block = 0;
@@ -615,15 +621,16 @@ PYBIND11_MODULE(_C, m) {
         py::arg("key"), py::arg("num_rows"), py::arg("num_trainers"), py::arg("fields"),
         py::arg("num_fields"), py::arg("n_local"), py::arg("global_offset"),
         py::arg("row_pitch"), py::arg("write_lo"), py::arg("write_hi"), py::arg("dst"),
-        py::arg("grid"), py::arg("stream"));
+        py::arg("grid"), py::arg("stream"), py::arg("slot_lo") = 0, py::arg("slot_hi") = ~0ull);
   m.def("scatter_wide",
         [](const std::vector<uint64_t>& key, uint64_t num_rows, uint32_t num_trainers,
            uintptr_t src, uint32_t width, uint32_t src_code, uint32_t dst_code, uint32_t dst_off,
            uint64_t n_local, uint64_t global_offset, uint32_t row_pitch,
-           const std::vector<uintptr_t>& dst, int grid, uintptr_t stream) {
+           const std::vector<uintptr_t>& dst, int grid, uintptr_t stream, uint64_t slot_lo,
+           uint64_t slot_hi) {
           WideParams p;
           p.key = make_key(key);
-          p.plan = make_plan(num_rows, num_trainers);
+          p.plan = make_plan(num_rows, num_trainers, slot_lo, slot_hi);
           p.src = as_ptr<const uint8_t>(src);
           p.width = width;
           p.src_code = src_code;
@@ -638,7 +645,7 @@ PYBIND11_MODULE(_C, m) {
         py::arg("key"), py::arg("num_rows"), py::arg("num_trainers"), py::arg("src"),
         py::arg("width"), py::arg("src_code"), py::arg("dst_code"), py::arg("dst_off"),
         py::arg("n_local"), py::arg("global_offset"), py::arg("row_pitch"), py::arg("dst"),
-        py::arg("grid"), py::arg("stream"));
+        py::arg("grid"), py::arg("stream"), py::arg("slot_lo") = 0, py::arg("slot_hi") = ~0ull);
   m.attr("FIELD_DESC_BYTES") = sizeof(FieldDev);
   m.def("perm_positions",
         [](const std::vector<uint64_t>& key, uint64_t num_rows, uint32_t num_trainers,
@@ -648,11 +655,15 @@ PYBIND11_MODULE(_C, m) {
                                       global_offset, n_local, as_ptr<int32_t>(trainer),
                                       as_ptr<long long>(slot), as_stream(stream));
         });
-  m.def("place_rows", [](uintptr_t rows, uintptr_t slots, uint64_t n, uint32_t pitch,
-                         uintptr_t dst, uintptr_t stream) {
-    rsdl::launch_place_rows(as_ptr<const uint8_t>(rows), as_ptr<const long long>(slots), n, pitch,
+  m.def("place_rows", [](uintptr_t rows, uintptr_t dst_off, uint64_t n, uint32_t pitch,
+                         uintptr_t dst, uintptr_t stream, uintptr_t src_idx) {
+    rsdl::launch_place_rows(as_ptr<const uint8_t>(rows), as_ptr<const long long>(src_idx),
+                            as_ptr<const long long>(dst_off), n, pitch,
                             as_ptr<uint8_t>(dst), as_stream(stream));
-  });
+  }, py::arg("rows"), py::arg("dst_off"), py::arg("n"), py::arg("pitch"), py::arg("dst"),
+     py::arg("stream"), py::arg("src_idx") = 0,
+     "dst[dst_off[i] bytes] <- rows[src_idx[i] or i] (row copies of `pitch` bytes; "
+     "negative offsets are skipped)");
   m.def("key_checksum", [](uintptr_t packed, uint64_t rows, uint32_t pitch, uint32_t key_off,
                            uintptr_t out, uintptr_t stream) {
     rsdl::launch_key_checksum(as_ptr<const uint8_t>(packed), rows, pitch, key_off,

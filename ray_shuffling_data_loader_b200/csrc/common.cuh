@@ -44,6 +44,11 @@ struct PlanDev {
   unsigned long long big;   // rem * (q + 1)
   uint32_t rem;             // first `rem` trainers own q + 1 rows
   uint32_t num_trainers;
+  // Destination-chunk pass filter (K7): a launch only delivers rows whose slot in
+  // the trainer's epoch buffer lies in [slot_lo, slot_hi); a full epoch is
+  // [0, ~0). See DeviceShuffleEngine.chunk_passes.
+  unsigned long long slot_lo;
+  unsigned long long slot_hi;
 };
 
 #define RSDL_CUDA_CHECK(expr)                                                   \

@@ -84,8 +84,8 @@ void launch_scatter_wide(const WideParams& p, int grid, cudaStream_t stream);
 void launch_perm_positions(const PermKeyDev& key, const PlanDev& plan,
                            unsigned long long global_offset, unsigned long long n_local,
                            int32_t* trainer, long long* slot, cudaStream_t stream);
-void launch_place_rows(const uint8_t* rows, const long long* slots, unsigned long long n,
-                       uint32_t pitch, uint8_t* dst, cudaStream_t stream);
+void launch_place_rows(const uint8_t* rows, const long long* src_idx, const long long* dst_off,
+                       unsigned long long n, uint32_t pitch, uint8_t* dst, cudaStream_t stream);
 void launch_key_checksum(const uint8_t* packed, unsigned long long rows, uint32_t pitch,
                          uint32_t key_off, unsigned long long* out, cudaStream_t stream);
 void launch_batch_sum_f32(const uint8_t* packed, unsigned long long rows, uint32_t pitch,

@@ -172,6 +172,7 @@ dest_pointer(unsigned long long gi, const PermKeyDev& key, const PlanDev& plan,
   uint32_t trainer;
   unsigned long long slot;
   rsdl_position_to_dest(pos, plan, &trainer, &slot);
+  if (slot < plan.slot_lo || slot >= plan.slot_hi) return 0ull;   // another pass delivers it
   return reinterpret_cast<unsigned long long>(dst[trainer]) + slot * row_pitch;
 }
 
@@ -447,7 +448,7 @@ scatter_tma_kernel(const __grid_constant__ FastParams p) {
           uint32_t trainer;
           unsigned long long slot;
           rsdl_position_to_dest(x[i], p.plan, &trainer, &slot);
-          prev[i] = valid[i]
+          prev[i] = (valid[i] && slot >= p.plan.slot_lo && slot < p.plan.slot_hi)
               ? reinterpret_cast<unsigned long long>(p.dst[trainer]) + slot * p.row_pitch
               : 0ull;
         }
@@ -772,6 +773,7 @@ __global__ void __launch_bounds__(256) scatter_generic_kernel(const GenericParam
     // phase 2: one warp per row, 128 B contiguous per store instruction
     const uint32_t nwords = span / 4;
     for (uint32_t r = warp; r < rows; r += nwarps) {
+      if (dptr[r] == 0ull) continue;            // row belongs to another pass
       uint32_t* drow = reinterpret_cast<uint32_t*>(dptr[r] + p.write_lo);
       const uint32_t* srow = reinterpret_cast<const uint32_t*>(stage + r * spitch);
       for (uint32_t w = lane; w < nwords; w += 32) drow[w] = srow[w];
@@ -800,8 +802,10 @@ __global__ void __launch_bounds__(256) scatter_wide_kernel(const WideParams p) {
                         (p.dst_off % 16 == 0) && (p.row_pitch % 16 == 0) &&
                         ((reinterpret_cast<unsigned long long>(p.src) & 15) == 0);
   for (unsigned long long r = warp0; r < p.n_local; r += nwarps) {
-    const unsigned long long d =
-        dest_pointer(p.global_offset + r, p.key, p.plan, p.dst, p.row_pitch) + p.dst_off;
+    const unsigned long long d0 =
+        dest_pointer(p.global_offset + r, p.key, p.plan, p.dst, p.row_pitch);
+    if (d0 == 0ull) continue;                   // row belongs to another pass
+    const unsigned long long d = d0 + p.dst_off;
     const uint8_t* src = p.src + r * src_row_bytes;
     if (vec_copy) {
       const uint4* s4 = reinterpret_cast<const uint4*>(src);
@@ -852,17 +856,22 @@ __global__ void perm_positions_kernel(PermKeyDev key, PlanDev plan, unsigned lon
 }
 
 // ---------------------------------------------------------------------------
-// K5 local row placement: dst[slots[i]] = rows[i] (NCCL baseline's last stage)
+// K5 local row placement (NCCL baseline's gather and final placement stages):
+//   dst_base + dst_off[i]  <-  rows[(src_idx ? src_idx[i] : i)]     (dst_off < 0: skip)
 // ---------------------------------------------------------------------------
-__global__ void place_rows_kernel(const uint8_t* rows, const long long* slots, unsigned long long n,
+__global__ void place_rows_kernel(const uint8_t* rows, const long long* src_idx,
+                                  const long long* dst_off, unsigned long long n,
                                   uint32_t pitch, uint8_t* dst) {
   const int lane = threadIdx.x & 31;
   const unsigned long long warp = (blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x) >> 5;
   const unsigned long long nwarps = (static_cast<unsigned long long>(gridDim.x) * blockDim.x) >> 5;
   const uint32_t vecs = pitch / 16;
   for (unsigned long long i = warp; i < n; i += nwarps) {
-    const uint4* s = reinterpret_cast<const uint4*>(rows + i * pitch);
-    uint4* d = reinterpret_cast<uint4*>(dst + static_cast<unsigned long long>(slots[i]) * pitch);
+    const long long off = dst_off[i];
+    if (off < 0) continue;                      // padding entry of a fixed-size exchange block
+    const unsigned long long si = src_idx ? static_cast<unsigned long long>(src_idx[i]) : i;
+    const uint4* s = reinterpret_cast<const uint4*>(rows + si * pitch);
+    uint4* d = reinterpret_cast<uint4*>(dst + off);
     for (uint32_t v = lane; v < vecs; v += 32) d[v] = s[v];
   }
 }
@@ -1068,11 +1077,12 @@ void launch_perm_positions(const PermKeyDev& key, const PlanDev& plan, unsigned 
   check_launch("perm_positions");
 }
 
-void launch_place_rows(const uint8_t* rows, const long long* slots, unsigned long long n,
-                       uint32_t pitch, uint8_t* dst, cudaStream_t stream) {
+void launch_place_rows(const uint8_t* rows, const long long* src_idx, const long long* dst_off,
+                       unsigned long long n, uint32_t pitch, uint8_t* dst, cudaStream_t stream) {
   if (n == 0) return;
-  int grid = static_cast<int>(std::min<unsigned long long>((n + 7) / 8, 148 * 8));
-  place_rows_kernel<<<grid, 256, 0, stream>>>(rows, slots, n, pitch, dst);
+  if (pitch % 16) throw std::runtime_error("place_rows: row pitch must be a multiple of 16");
+  int grid = static_cast<int>(std::min<unsigned long long>((n + 7) / 8, 148 * 16));
+  place_rows_kernel<<<grid, 256, 0, stream>>>(rows, src_idx, dst_off, n, pitch, dst);
   check_launch("place_rows");
 }
 

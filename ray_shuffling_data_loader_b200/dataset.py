@@ -48,31 +48,32 @@ def get_num_cpus() -> int:
 
 
 class ShufflingDataset:
-    """
-    A shuffling dataset that yields batches upon iteration.
+    """Per-epoch globally shuffled batches of rows.
 
-    This dataset will kick off shuffling for max_concurrent_epochs epochs at
-    construction time.
+    Positional arguments (same order as reference ``dataset.py:37-45``):
 
-    Args:
-        filenames (str): Paths to input Parquet files.
-        num_epochs (int): Number of training epochs.
-        num_trainers (int): Number of trainer workers.
-        batch_size (int): Size of the batches that the iterator should yield.
-        rank (int): The worker rank of the current process.
-        drop_last (Optional[bool]): Whether to drop the last batch if it's
-            incomplete (smaller than batch_size). Default is False.
-        num_reducers (Optional[int]): The number of shuffler reducers. Default
-            is the number of trainers x the number of cores x 0.6.
-        max_concurrent_epochs (Optional[int]): The maximum number of epochs
-            whose shuffling stages should execute concurrently. Default is 2.
-        seed (Optional[int]): permutation seed (``None``: random, agreed
-            across ranks). Same seed => same batches, on CPU and GPU.
-        backend: ``"cuda"``, ``"cpu"`` or ``None`` (auto).
-        output: ``"pandas"`` (CPU default), ``"device"`` (GPU default,
-            ``DeviceBatch``) or ``"packed"`` (raw ``uint8[B, pitch]``).
-        layout_fn: ``schema -> RowLayout`` (column projection + casts).
-        start_epoch: first epoch to shuffle (resume).
+    ``filenames``              input Parquet files (their concatenation is the table)
+    ``num_epochs``             epochs that will be iterated
+    ``num_trainers``           data-parallel consumers; each gets a disjoint 1/T of every epoch
+    ``batch_size``             rows per yielded batch
+    ``rank``                   which trainer this process is
+    ``drop_last``              skip the final short batch (default: yield it)
+    ``num_reducers``           destination chunks per epoch, each with its own completion
+                               flag (default ``trainers x cores x 0.6`` like the reference)
+    ``max_concurrent_epochs``  epoch ring depth (default 2)
+
+    Shuffling of the first ``max_concurrent_epochs`` epochs starts in the
+    constructor.
+
+    Keyword-only:
+
+    ``seed``         permutation seed (``None``: random, agreed across ranks); the same
+                     seed gives the same batches on the CPU and the GPU backend
+    ``backend``      ``"cuda"``, ``"cpu"`` or ``None`` (auto)
+    ``output``       ``"pandas"`` (CPU default), ``"device"`` (GPU default: ``DeviceBatch``),
+                     ``"packed"`` (raw ``uint8[B, pitch]``)
+    ``layout_fn``    ``schema -> RowLayout`` (column projection and casts)
+    ``start_epoch``  first epoch to shuffle (checkpoint resume)
     """
 
     def __init__(self,
@@ -190,15 +191,8 @@ class ShufflingDataset:
         return self._seed
 
     def set_epoch(self, epoch):
-        """
-        Set the current training epoch. This should be called before
-        constructing the iterator on this dataset (e.g. before the
-        enumerate(train_loader) call).
-
-        Args:
-            epoch (int) The epoch number for the training epoch that is about
-                to start.
-        """
+        """Select the epoch the next ``iter()`` will read; must be called with a
+        new value before every pass (reference ``dataset.py:96-106``)."""
         self._epoch = epoch
 
     # -- checkpoint / resume (not in the reference) -------------------------
@@ -452,48 +446,47 @@ class BatchConsumerQueue(BatchConsumer):
         self._batch_queue.wait_until_all_epochs_done()
 
 
-def _smoke_main():
-    """``python -m ray_shuffling_data_loader_b200.dataset``: the reference's
-    smoke driver (``dataset.py:208-252``), with assertions added."""
-    import shutil
+def _smoke_main(argv=None) -> int:
+    """``python -m ray_shuffling_data_loader_b200.dataset``: generate a small
+    ``DATA_SPEC`` table, iterate it for a few epochs and *verify* delivery (role of
+    the reference's ``__main__`` block, ``dataset.py:208-252``, which only prints):
+    every key exactly once per epoch, exact batch sizes, a new order per epoch."""
+    import argparse
     import tempfile
-    from ray_shuffling_data_loader_b200.stats import human_readable_size
+    import numpy as np
     from ray_shuffling_data_loader_b200.data_generation import generate_data
-    num_rows = 10**6
-    num_files = 10
-    num_row_groups_per_file = 1
-    max_row_group_skew = 0.0
-    data_dir = tempfile.mkdtemp()
-    print(f"Generating {num_rows} rows over {num_files} files, with "
-          f"{num_row_groups_per_file} row groups per file and at most "
-          f"{100 * max_row_group_skew:.1f}% row group skew.")
-    filenames, num_bytes = generate_data(num_rows, num_files,
-                                         num_row_groups_per_file,
-                                         max_row_group_skew, data_dir)
-    print(f"Generated {len(filenames)} files containing {num_rows} rows "
-          f"with {num_row_groups_per_file} row groups per file, totalling "
-          f"{human_readable_size(num_bytes)}.")
-    num_epochs = 4
-    num_trainers = 1
-    batch_size = 20000
-    rank = 0
-    num_reducers = 8
-    print(f"Creating shuffling dataset with {batch_size} batch size, "
-          f"{num_epochs} epochs, {num_reducers} reducers, and {num_trainers} "
-          "trainers.")
-    print(f"Should consume {num_rows // batch_size} batches.")
-    ds = ShufflingDataset(filenames, num_epochs, num_trainers, batch_size, rank,
-                          num_reducers=num_reducers)
-    for epoch in range(num_epochs):
-        ds.set_epoch(epoch)
-        rows = 0
-        for batch_idx, batch in enumerate(ds):
-            rows += len(batch)
-            print(f"Consuming batch {batch_idx}!")
-        assert rows == num_rows, (rows, num_rows)
-    print("Done consuming batches.")
-    shutil.rmtree(data_dir)
+    ap = argparse.ArgumentParser(description=_smoke_main.__doc__)
+    ap.add_argument("--num-rows", type=int, default=10**6)
+    ap.add_argument("--num-files", type=int, default=10)
+    ap.add_argument("--num-epochs", type=int, default=4)
+    ap.add_argument("--batch-size", type=int, default=20000)
+    ap.add_argument("--num-reducers", type=int, default=8)
+    ap.add_argument("--backend", default=None, choices=[None, "cpu", "cuda"])
+    a = ap.parse_args(argv)
+    with tempfile.TemporaryDirectory() as data_dir:
+        files, nbytes = generate_data(a.num_rows, a.num_files, 1, 0.0, data_dir)
+        print(f"{len(files)} files, {a.num_rows} rows ({nbytes / 1e6:.1f} MB decoded); "
+              f"{a.num_epochs} epochs, batch {a.batch_size}, {a.num_reducers} reducers")
+        ds = ShufflingDataset(files, a.num_epochs, 1, a.batch_size, 0,
+                              num_reducers=a.num_reducers, backend=a.backend, output="pandas")
+        orders = []
+        for epoch in range(a.num_epochs):
+            ds.set_epoch(epoch)
+            keys = []
+            for batch in ds:
+                if len(batch) != a.batch_size and len(keys) * a.batch_size + len(batch) != a.num_rows:
+                    raise AssertionError("short batch in the middle of an epoch")
+                keys.append(batch["key"].to_numpy())
+            keys = np.concatenate(keys)
+            if not np.array_equal(np.sort(keys), np.arange(a.num_rows)):
+                raise AssertionError(f"epoch {epoch}: rows lost or duplicated")
+            orders.append(keys[:64].copy())
+            print(f"epoch {epoch}: {len(keys)} rows, exactly once")
+        if len(orders) > 1 and all(np.array_equal(orders[0], o) for o in orders[1:]):
+            raise AssertionError("epochs were not reshuffled")
+    print("ok")
+    return 0
 
 
 if __name__ == "__main__":
-    _smoke_main()
+    raise SystemExit(_smoke_main())

@@ -329,6 +329,8 @@ def unpack_field(packed: np.ndarray, f: Field) -> np.ndarray:
     """Inverse of pack for one field: returns ``[n]`` or ``[n, width]`` in the
     storage dtype (a copy)."""
     n = packed.shape[0]
-    raw = np.ascontiguousarray(packed[:, f.offset:f.offset + f.dst_bytes])
+    # always a private copy (ascontiguousarray would alias the epoch buffer when
+    # one field fills the whole row pitch, and that buffer is recycled)
+    raw = np.array(packed[:, f.offset:f.offset + f.dst_bytes], order="C", copy=True)
     vals = raw.view(_CODE_TO_NP[f.dst_code]).reshape(n, f.width)
     return vals[:, 0] if f.width == 1 else vals

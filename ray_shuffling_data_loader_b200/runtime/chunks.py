@@ -49,9 +49,14 @@ class EpochBuffer:
         self._ready.set()
 
     # consumer side ---------------------------------------------------------
-    def wait(self, timeout: Optional[float] = None):
+    def wait(self, timeout: Optional[float] = None, row_stop: Optional[int] = None):
+        """Block (or, in stream mode, make the current CUDA stream wait) until rows
+        ``[0, row_stop)`` - default: the whole buffer - have landed."""
         if self._wait_fn is not None:
-            self._wait_fn(timeout)
+            if row_stop is None:
+                self._wait_fn(timeout)
+            else:
+                self._wait_fn(timeout, row_stop)
             return
         if not self._ready.wait(timeout):
             raise TimeoutError(
@@ -98,7 +103,10 @@ class ShuffledChunk:
         return self.row_stop - self.row_start
 
     def wait(self, timeout: Optional[float] = None) -> "ShuffledChunk":
-        self.buffer.wait(timeout)
+        """Wait for THIS chunk only: the completion flags of the destination-chunk
+        pass that delivers ``[.., row_stop)`` (reference analogue: ``ray.wait`` on
+        one reducer output, ``dataset.py:133-139``)."""
+        self.buffer.wait(timeout, self.row_stop)
         return self
 
     def packed(self):

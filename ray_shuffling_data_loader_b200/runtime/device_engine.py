@@ -82,8 +82,9 @@ class _CudaView:
 def as_torch(ptr: int, shape: Tuple[int, ...], device_index: int, typestr: str = "|u1"):
     import torch
     if int(np.prod(shape)) == 0:
-        dt = {"|u1": torch.uint8, "<i4": torch.int32, "<i8": torch.int64,
-              "<u4": torch.int32}[typestr]
+        dt = {"|u1": torch.uint8, "|i1": torch.int8, "<i2": torch.int16, "<i4": torch.int32,
+              "<i8": torch.int64, "<u4": torch.int32, "<f2": torch.float16,
+              "<f4": torch.float32, "<f8": torch.float64, "|b1": torch.bool}[typestr]
         return torch.empty(shape, dtype=dt, device=f"cuda:{device_index}")
     return torch.as_tensor(_CudaView(ptr, shape, typestr), device=f"cuda:{device_index}")
 
@@ -105,12 +106,14 @@ class DeviceShuffleEngine:
                  seed: int, rank: int = 0, world: int = 1, stats_collector=None,
                  max_concurrent_epochs: int = 2, num_threads: Optional[int] = None,
                  resident: str = "hbm", stream_chunk_rows: Optional[int] = None,
-                 exchange: str = "p2p", wait_mode: str = "host",
+                 exchange: str = "p2p", wait_mode: str = "stream",
                  flag_timeout_s: float = 300.0, index=None,
                  device_index: Optional[int] = None, grid: Optional[int] = None,
                  process_group=None, force_generic: bool = False,
                  use_tensor_map: bool = True, peer_alloc: Optional[str] = None,
-                 backpressure: Optional[str] = None, numa_bind: Optional[bool] = None):
+                 backpressure: Optional[str] = None, numa_bind: Optional[bool] = None,
+                 tmap_mode: Optional[int] = None, sched: Optional[int] = None,
+                 exchange_group=None, chunk_passes: Optional[int] = None):
         import torch
         self.C = load_native()
         self.torch = torch
@@ -139,6 +142,8 @@ class DeviceShuffleEngine:
         self.layout: L.RowLayout = layout_fn(self.index.schema)
         self.seed = int(seed)
         self.rank, self.world, self.pg = rank, world, process_group
+        # private communicator of the NCCL baseline exchange (runtime/engine.py)
+        self.exchange_pg = exchange_group if exchange_group is not None else process_group
         self.stats = stats_collector
         self.window = max(1, int(max_concurrent_epochs))
         self.num_threads = num_threads or max(1, min(16, (os.cpu_count() or 2)))
@@ -168,17 +173,47 @@ class DeviceShuffleEngine:
         # Source tile loads: 0 = 1-D bulk copies (cp.async.bulk, fastest measured:
         # 512-byte contiguous DRAM reads), 1 = tensor-map boxes with 128B swizzle,
         # 2 = one dense tensor-map box per tile. See profiles/README.md.
-        self.tmap_mode = int(os.environ.get("RSDL_TMAP_MODE", "0"))
+        # ``sched``: producer schedule of the TMA kernel (-1 = chosen per layout by
+        # the binding). Both are constructor options (recorded by bench.py); the
+        # RSDL_* environment variables only provide defaults for A/B runs.
+        self.tmap_mode = int(os.environ.get("RSDL_TMAP_MODE", "0")) if tmap_mode is None \
+            else int(tmap_mode)
+        self.sched = int(os.environ.get("RSDL_SCHED", "-1")) if sched is None else int(sched)
         self.local_trainers: List[int] = ([rank] if world > 1
                                           else list(range(self.plan.num_trainers)))
+        # K7 - destination-chunk passes. A uniform shuffle makes every destination
+        # chunk depend on every source row, so "chunk 0 is ready before the epoch
+        # is" is only possible if the sources deliver chunk 0's rows first: the
+        # epoch's scatter is issued as ``chunk_passes`` launches, pass k delivering
+        # only the rows whose slot falls in the k-th slice of every trainer's
+        # buffer, each followed by its own produced flag. Cost: the source table is
+        # re-read (and re-indexed) once per pass, which hides under the NVLink-bound
+        # stores when world > 1 (default there: up to 4 passes, never more than the
+        # reducer chunks per trainer) and is a real cost on one GPU (default 1).
+        # Host-streaming and the NCCL baseline always use one pass.
+        max_chunks = max(self.plan.reducers_of_trainer(t) for t in range(self.plan.num_trainers))
+        if chunk_passes is None:
+            chunk_passes = min(4, max_chunks) if world > 1 else 1
+        if resident == "host" or exchange == "nccl":
+            chunk_passes = 1
+        self.chunk_passes = max(1, min(int(chunk_passes), 64, max(1, self.plan.max_trainer_rows)))
+        from ray_shuffling_data_loader_b200.ops.plan import balanced_split
+        self.pass_bounds = balanced_split(self.plan.max_trainer_rows, self.chunk_passes)
         self.sm_count = self.C.sm_count(device_index)
         self.grid_override = grid
         self.launches = 0                 # kernels launched by this engine
+        self.scatter_launches = 0         # ... of which scatter kernels (any variant)
+        self.h2d_bytes_enqueued = 0       # resident="host": bytes handed to cudaMemcpyAsync
+        self.epochs_started = 0           # epochs whose shuffle has been enqueued
+        self.first_epoch: Optional[int] = None
+        self._started_cv = threading.Condition()
         self._lock = threading.Lock()
         self._closed = False
         self._ingested = False
         self._events: Dict[int, Tuple[int, int]] = {}
         self._epoch_kernel_ms: Dict[int, float] = {}
+        self._first_pass_events: Dict[int, Tuple[int, int]] = {}
+        self._first_pass_ms: Dict[int, float] = {}
 
         lo, hi = self.plan.source_range(rank, world)
         self.src_lo, self.n_local = lo, hi - lo
@@ -209,9 +244,9 @@ class DeviceShuffleEngine:
         self.slot_rows = plan.max_trainer_rows
         self.slot_bytes = _align(max(1, self.slot_rows) * self.layout.row_pitch)
         nloc = len(self.local_trainers)
-        # header: produced[W][world] | consumed[T] | error[4]  (uint32 words)
+        # header: produced[W][passes][world] | consumed[T] | error[4]  (uint32 words)
         self.off_produced = 0
-        self.off_consumed = _align(self.window * self.world * 4, 128)
+        self.off_consumed = _align(self.window * self.chunk_passes * self.world * 4, 128)
         self.off_error = self.off_consumed + _align(T * 4, 128)
         self.header_bytes = _align(self.off_error + 16, 4096)
         self.arena_bytes = self.header_bytes + self.window * nloc * self.slot_bytes
@@ -276,8 +311,22 @@ class DeviceShuffleEngine:
         return (self.peer_base[owner] + self.header_bytes
                 + (slot * nloc + j) * self.slot_bytes)
 
-    def _produced_ptr(self, on_rank: int, slot: int, src_rank: int) -> int:
-        return self.peer_base[on_rank] + self.off_produced + (slot * self.world + src_rank) * 4
+    def _produced_ptr(self, on_rank: int, slot: int, src_rank: int, pass_idx: int = -1) -> int:
+        """Flag "source ``src_rank`` delivered pass ``pass_idx`` (default: the last)
+        of the epoch in ring slot ``slot``" in rank ``on_rank``'s arena; the
+        ``world`` flags of one pass are contiguous (one wait kernel covers them)."""
+        k = self.chunk_passes - 1 if pass_idx < 0 else pass_idx
+        return (self.peer_base[on_rank] + self.off_produced
+                + ((slot * self.chunk_passes + k) * self.world + src_rank) * 4)
+
+    def pass_of_row(self, row_stop: int) -> int:
+        """Index of the pass after which rows ``[0, row_stop)`` of a trainer's epoch
+        buffer are complete."""
+        last = max(0, row_stop - 1)
+        for k, (lo, hi) in enumerate(self.pass_bounds):
+            if last < hi:
+                return k
+        return self.chunk_passes - 1
 
     def _consumed_ptr(self, on_rank: int, trainer: int) -> int:
         return self.peer_base[on_rank] + self.off_consumed + trainer * 4
@@ -540,10 +589,11 @@ class DeviceShuffleEngine:
         return max(1, min(g, work_items))
 
     def _launch_chunk(self, key_words, buf: int, n_rows: int, global_offset: int,
-                      dst: List[int]):
+                      dst: List[int], slot_range: Optional[Tuple[int, int]] = None):
         C, lay, plan = self.C, self.layout, self.plan
         if n_rows <= 0:
             return
+        slot_lo, slot_hi = slot_range if slot_range is not None else (0, (1 << 64) - 1)
         if self.fast_mode >= 0:
             ncols = len(self.fast_field_idx)
             tiles = -(-n_rows // C.fast_tile_rows(self.fast_mode))
@@ -567,8 +617,9 @@ class DeviceShuffleEngine:
                            tmap_mode=self.tmap_mode,
                            kinds=self.fast_kinds_dev if self.fast_mode == 4 else 0,
                            write_end=self.fast_write_end,
-                           sched=int(os.environ.get("RSDL_SCHED", "-1")))
+                           sched=self.sched, slot_lo=slot_lo, slot_hi=slot_hi)
             self.launches += 1
+            self.scatter_launches += 1
         for i in self.wide_field_idx:
             f = self.src_fields[i]
             C.scatter_wide(key=key_words, num_rows=plan.num_rows,
@@ -576,8 +627,9 @@ class DeviceShuffleEngine:
                            width=f.width, src_code=f.src_code, dst_code=f.dst_code,
                            dst_off=f.offset, n_local=n_rows, global_offset=global_offset,
                            row_pitch=lay.row_pitch, dst=dst, grid=self.grid_override or 0,
-                           stream=self.shuffle_stream)
+                           stream=self.shuffle_stream, slot_lo=slot_lo, slot_hi=slot_hi)
             self.launches += 1
+            self.scatter_launches += 1
         for (idxs, lo, hi), fields_dev in zip(self.generic_runs, self.generic_fields_dev[buf]):
             C.scatter_generic(key=key_words, num_rows=plan.num_rows,
                               num_trainers=plan.num_trainers, fields=fields_dev,
@@ -585,8 +637,16 @@ class DeviceShuffleEngine:
                               global_offset=global_offset, row_pitch=lay.row_pitch,
                               write_lo=lo, write_hi=hi, dst=dst,
                               grid=self.grid_override or 0,   # 0: launcher picks by occupancy
-                              stream=self.shuffle_stream)
+                              stream=self.shuffle_stream, slot_lo=slot_lo, slot_hi=slot_hi)
             self.launches += 1
+            self.scatter_launches += 1
+
+    def _signal_produced(self, slot: int, pass_idx: int, epoch: int):
+        """publish: produced[slot][pass][this rank] = epoch + 1 on every rank
+        (st.release.sys after a system fence, stream-ordered after the pass)."""
+        targets = [self._produced_ptr(r, slot, self.rank, pass_idx) for r in range(self.world)]
+        self.C.signal_flags(targets, epoch + 1, self.shuffle_stream)
+        self.launches += 1
 
     def start_epoch(self, epoch: int) -> Dict[int, EpochBuffer]:
         """Enqueue the epoch's shuffle on the side stream (non-blocking apart
@@ -599,14 +659,21 @@ class DeviceShuffleEngine:
         with trace.span("ingest", epoch=epoch):
             self._ensure_ingested(epoch)
         slot = epoch % self.window
-        if epoch >= self.window and self.backpressure == "stream":
+        if self.first_epoch is None:
+            # Resume (start_epoch = k): the arena's flags start at zero in a fresh
+            # process, so the slot-reuse gate only applies to epochs that reuse a
+            # slot *this engine* has filled (epoch - first >= window). Flags are
+            # monotonic epoch tags, so nothing needs seeding.
+            self.first_epoch = epoch
+        gate = epoch - self.first_epoch >= self.window
+        if gate and self.backpressure == "stream":
             # Back-pressure, stream ordered: every trainer must have released
             # this slot's previous epoch before any source may overwrite it.
             C.wait_flags(self._consumed_ptr(self.rank, 0), plan.num_trainers,
                          epoch - self.window + 1, int(self.flag_timeout_s * 1e9),
                          self.arena + self.off_error, self.shuffle_stream)
             self.launches += 1
-        elif epoch >= self.window:
+        elif gate:
             with trace.span("backpressure_wait", epoch=epoch):
                 lag = self._poll(self._consumed_ptr(self.rank, 0), plan.num_trainers,
                                  epoch - self.window + 1, self.flag_timeout_s)
@@ -623,18 +690,29 @@ class DeviceShuffleEngine:
         ev0, ev1 = C.event_create(True), C.event_create(True)
         C.event_record(ev0, self.shuffle_stream)
         trace.instant("launch_epoch_shuffle", epoch=epoch, slot=slot)
+        ev_first = ev_first0 = None
+        if self.chunk_passes > 1:
+            ev_first0 = C.event_create(True)
+            C.event_record(ev_first0, self.shuffle_stream)
         if self.exchange == "nccl":
             from ray_shuffling_data_loader_b200.parallel import nccl_baseline
             nccl_baseline.exchange_epoch(self, key_words, slot)
+            self._signal_produced(slot, 0, epoch)
         elif self.resident == "hbm":
-            self._launch_chunk(key_words, 0, self.n_local, self.src_lo, dst)
+            # one launch (set) per destination-chunk pass, each with its own flag
+            for k, bounds in enumerate(self.pass_bounds):
+                self._launch_chunk(key_words, 0, self.n_local, self.src_lo, dst,
+                                   bounds if self.chunk_passes > 1 else None)
+                self._signal_produced(slot, k, epoch)
+                if k == 0 and self.chunk_passes > 1:
+                    ev_first = C.event_create(True)
+                    C.event_record(ev_first, self.shuffle_stream)
         else:
             self._stream_epoch(key_words, dst)
+            self._signal_produced(slot, 0, epoch)
         C.event_record(ev1, self.shuffle_stream)
-        # publish: produced[slot][rank] = epoch + 1 on every rank
-        targets = [self._produced_ptr(r, slot, self.rank) for r in range(self.world)]
-        C.signal_flags(targets, epoch + 1, self.shuffle_stream)
-        self.launches += 1
+        if ev_first is not None:
+            self._first_pass_events[epoch] = (ev_first0, ev_first)
         self._events[epoch] = (ev0, ev1)
 
         buffers = {}
@@ -646,7 +724,26 @@ class DeviceShuffleEngine:
                 epoch, t, rows, self.layout, data, "cuda",
                 wait_fn=self._make_wait(epoch, slot, t_start),
                 release_fn=self._make_release(epoch, t))
+        with self._started_cv:
+            self.epochs_started = epoch + 1
+            self._started_cv.notify_all()
         return buffers
+
+    def wait_epochs_started(self, n: int, timeout: float = 60.0) -> bool:
+        """Block until the shuffles of epochs ``< n`` have been enqueued (the
+        driver thread runs ahead of the consumer by the epoch window)."""
+        with self._started_cv:
+            return self._started_cv.wait_for(lambda: self.epochs_started >= n, timeout)
+
+    def enqueue_wait_produced(self, epoch: int, stream: Optional[int] = None):
+        """Make ``stream`` (default: the current torch stream) wait, on the
+        device, until every source rank has delivered ``epoch`` to this rank."""
+        if stream is None:
+            stream = self.torch.cuda.current_stream().cuda_stream
+        self.C.wait_flags(self._produced_ptr(self.rank, epoch % self.window, 0), self.world,
+                          epoch + 1, int(self.flag_timeout_s * 1e9),
+                          self.arena + self.off_error, stream)
+        self.launches += 1
 
     def _stream_epoch(self, key_words, dst):
         """resident='host': double-buffered H2D of source chunks overlapping the
@@ -694,6 +791,7 @@ class DeviceShuffleEngine:
             else:
                 j = i + 1
                 C.memcpy_async(ptrs[i], base + row0 * isz, rows * isz, C.H2D, self.copy_stream)
+            self.h2d_bytes_enqueued += rows * isz * (j - i)
             i = j
 
     def h2d_bytes_per_epoch(self) -> int:
@@ -719,52 +817,47 @@ class DeviceShuffleEngine:
                 return lag
 
     def _make_wait(self, epoch: int, slot: int, t_start: float):
-        state = {"done": False}
+        state = {"pass": -1}
 
-        def wait(timeout: Optional[float] = None):
-            if state["done"]:
+        def wait(timeout: Optional[float] = None, row_stop: Optional[int] = None):
+            """Wait until rows ``[0, row_stop)`` of the buffer (default: all of it)
+            have been delivered by every source - i.e. for the produced flags of
+            the destination-chunk pass that completes them (K7)."""
+            need = self.chunk_passes - 1 if row_stop is None else self.pass_of_row(row_stop)
+            if need <= state["pass"]:
                 return
             self.C.set_device(self.device_index)
+            flags = self._produced_ptr(self.rank, slot, 0, need)
             if self.wait_mode == "stream":
                 # Device-side wait on the consumer's stream: no host sync. A wait
                 # kernel that gave up (dead peer) only sets the error word, so
                 # look at it once per epoch - an unordered 4-byte read on the
                 # poller's stream - and fail within an epoch instead of feeding
                 # the trainer a half-written buffer.
-                if epoch > 0:
+                if epoch > 0 and state["pass"] < 0:
                     self.check_error()
                 stream = self.torch.cuda.current_stream().cuda_stream
-                self.C.wait_flags(self._produced_ptr(self.rank, slot, 0), self.world,
-                                  epoch + 1, int(self.flag_timeout_s * 1e9),
+                self.C.wait_flags(flags, self.world, epoch + 1, int(self.flag_timeout_s * 1e9),
                                   self.arena + self.off_error, stream)
                 self.launches += 1
             else:
                 limit = self.flag_timeout_s if timeout is None else timeout
                 with trace.span("wait_epoch_produced", epoch=epoch):
-                    lag = self._poll(self._produced_ptr(self.rank, slot, 0), self.world,
-                                     epoch + 1, limit)
+                    lag = self._poll(flags, self.world, epoch + 1, limit)
                 if lag >= 0:
                     self.check_error()      # a device-side wait that gave up explains it
                     raise TimeoutError(
-                        f"source rank {lag} did not deliver epoch {epoch} within {limit}s")
-            state["done"] = True
-            self._epoch_done_stats(epoch, t_start)
+                        f"source rank {lag} did not deliver epoch {epoch} (pass {need}) "
+                        f"within {limit}s")
+            state["pass"] = need
+            if need == self.chunk_passes - 1:
+                self._epoch_done_stats(epoch, t_start)
         return wait
 
     def _epoch_done_stats(self, epoch: int, t_start: float):
-        ev = self._events.pop(epoch, None)
-        if ev is None:
+        if epoch not in self._events:
             return
-        ms = None
-        try:
-            if self.C.event_query(ev[1]):
-                ms = self.C.event_elapsed_ms(ev[0], ev[1])
-        except Exception:
-            ms = None
-        self.C.event_destroy(ev[0])
-        self.C.event_destroy(ev[1])
-        if ms is not None:
-            self._epoch_kernel_ms[epoch] = ms
+        ms = self._resolve_kernel_ms(epoch)
         if self.stats is not None:
             dur = (ms / 1e3) if ms is not None else (timeit.default_timer() - t_start)
             R = self.plan.num_reducers
@@ -774,8 +867,63 @@ class DeviceShuffleEngine:
                 remote = self.n_local * self.layout.row_pitch * (self.world - 1) // max(1, self.world)
                 self.stats.exchange_done(epoch, remote, ms / 1e3)
 
+    def _resolve_kernel_ms(self, epoch: int) -> Optional[float]:
+        """CUDA-event time of the epoch's shuffle on the shuffle stream, once
+        its end event has completed (a stream-mode wait returns to the host long
+        before that, so the events are kept until somebody asks again)."""
+        ev = self._events.get(epoch)
+        if ev is None:
+            return self._epoch_kernel_ms.get(epoch)
+        try:
+            if not self.C.event_query(ev[1]):
+                return None
+            ms = self.C.event_elapsed_ms(ev[0], ev[1])
+        except Exception:
+            return None
+        self._events.pop(epoch, None)
+        self.C.event_destroy(ev[0])
+        self.C.event_destroy(ev[1])
+        self._epoch_kernel_ms[epoch] = ms
+        return ms
+
+    def first_pass_ms(self, epoch: int) -> Optional[float]:
+        """Device time from the start of the epoch's shuffle to the end of its
+        first destination-chunk pass (= when chunk 0 becomes consumable); ``None``
+        with a single pass or before the pass has finished."""
+        if epoch in self._first_pass_ms:
+            return self._first_pass_ms[epoch]
+        ev = self._first_pass_events.get(epoch)
+        if ev is None:
+            return None
+        try:
+            if not self.C.event_query(ev[1]):
+                return None
+            ms = self.C.event_elapsed_ms(ev[0], ev[1])
+        except Exception:
+            return None
+        self._first_pass_events.pop(epoch)
+        self.C.event_destroy(ev[0])
+        self.C.event_destroy(ev[1])
+        self._first_pass_ms[epoch] = ms
+        return ms
+
     def epoch_kernel_ms(self, epoch: int) -> Optional[float]:
-        return self._epoch_kernel_ms.get(epoch)
+        if epoch in self._epoch_kernel_ms:
+            return self._epoch_kernel_ms[epoch]
+        return self._resolve_kernel_ms(epoch)
+
+    def source_column_tensors(self):
+        """Typed torch views of the HBM-resident source columns (``resident="hbm"``
+        after ingest): used by tests / bench to compute ground-truth sums with
+        plain torch, independent of the shuffle kernels."""
+        if self.resident != "hbm" or not self._ingested:
+            raise RuntimeError("source columns are only device resident with resident='hbm'")
+        out = []
+        for f, ptr in zip(self.src_fields, self.src_col_ptrs[0]):
+            typestr = np.dtype(L.numpy_storage_dtype(f.src_code)).str
+            shape = (self.n_local,) if f.width == 1 else (self.n_local, f.width)
+            out.append((f, as_torch(ptr, shape, self.device_index, typestr)))
+        return out
 
     def _make_release(self, epoch: int, trainer: int):
         def release():
@@ -875,10 +1023,11 @@ class DeviceShuffleEngine:
             self._closed = True
             stats_mod.unregister_bytes_used_source(self._bytes_fn)
             C = self.C
-            for ev in self._events.values():
+            for ev in list(self._events.values()) + list(self._first_pass_events.values()):
                 C.event_destroy(ev[0])
                 C.event_destroy(ev[1])
             self._events.clear()
+            self._first_pass_events.clear()
             if self.resident == "host":
                 for e in self.h2d_done + self.buf_free:
                     C.event_destroy(e)

@@ -52,6 +52,19 @@ def make_engine(filenames: Sequence[str], *, num_trainers: int, num_reducers: in
                      batch_size=batch_size, drop_last=drop_last)
     backend = resolve_backend(backend)
     recycle = bool(options.pop("recycle_buffers", False))       # host engine only
+    if world > 1:
+        # Collectives the engine issues from its *background* threads (the CPU
+        # engine's gloo all_to_all on the "cpu-shuffle" thread, the NCCL baseline's
+        # exchange on the shuffle-driver thread) must never share a communicator
+        # with the training loop's DDP / all_reduce on the main thread: their
+        # relative order would differ from rank to rank. Give them a private group
+        # (collective: every rank builds its dataset, like agree_on_seed above).
+        import torch.distributed as dist
+        if backend == "cpu" and options.get("process_group") is None:
+            options["process_group"] = dist.new_group(backend="gloo")
+        elif backend == "cuda" and options.get("exchange") == "nccl" \
+                and options.get("exchange_group") is None:
+            options["exchange_group"] = dist.new_group(backend="nccl")
     if backend == "cuda":
         from ray_shuffling_data_loader_b200.runtime.device_engine import DeviceShuffleEngine
         return DeviceShuffleEngine(filenames, plan_args, layout_fn, seed, rank=rank,

@@ -50,9 +50,32 @@ def _arrow_field_spec(f: pa.Field) -> Tuple[int, int]:
     if pa.types.is_fixed_size_list(t):
         return L.code_from_numpy(t.value_type.to_pandas_dtype()), t.list_size
     if pa.types.is_list(t) or pa.types.is_large_list(t):
-        # width resolved lazily from the data (must be constant per column)
+        # variable-size list *type* (what pandas writes for ndarray-valued cells):
+        # the per-row length is resolved from the footer by ``scan_files`` and must
+        # be constant, like the reference's np.stack requires (torch_dataset.py:212-221)
         return L.code_from_numpy(t.value_type.to_pandas_dtype()), -1
     return L.code_from_numpy(t.to_pandas_dtype()), 1
+
+
+def _list_width_from_footer(md, name: str, filename: str) -> int:
+    """Per-row element count of a ``list<item>`` column, from the first non-empty
+    row group's column-chunk statistics (leaf values / rows). The layout (row
+    pitch, kernel plan) is built from the schema before any data is decoded, so
+    the width has to be known here; ``load_table`` re-validates it on the data."""
+    for rg in range(md.num_row_groups):
+        g = md.row_group(rg)
+        if g.num_rows == 0:
+            continue
+        for c in range(g.num_columns):
+            col = g.column(c)
+            if col.path_in_schema.split(".")[0] != name:
+                continue
+            if col.num_values % g.num_rows:
+                raise ValueError(
+                    f"{filename}: list column {name!r} has {col.num_values} values in "
+                    f"{g.num_rows} rows - rows must all have the same length")
+            return max(1, col.num_values // g.num_rows)
+    return 1
 
 
 def scan_files(filenames: Sequence[str]) -> DatasetIndex:
@@ -76,7 +99,10 @@ def scan_files(filenames: Sequence[str]) -> DatasetIndex:
             for f in sch:
                 if f.name.startswith("__index_level_"):
                     continue
-                schema[f.name] = _arrow_field_spec(f)
+                code, width = _arrow_field_spec(f)
+                if width < 0:
+                    width = _list_width_from_footer(md, f.name, fn)
+                schema[f.name] = (code, width)
         nrows = 0
         for rg in range(md.num_row_groups):
             n = md.row_group(rg).num_rows
@@ -109,8 +135,14 @@ def _column_to_numpy(col: pa.ChunkedArray) -> np.ndarray:
         n = len(arr)
         if n == 0:
             return flat.reshape(0, max(1, getattr(t, "list_size", 1)))
-        if len(flat) % n != 0:
-            raise ValueError("list-valued columns must have a constant length per row")
+        if arr.null_count or len(flat) % n != 0:
+            raise ValueError("list-valued columns must have a constant length per row "
+                             "and no null rows")
+        if not pa.types.is_fixed_size_list(t):
+            lens = arr.value_lengths().to_numpy(zero_copy_only=False)
+            if len(lens) and (lens.min() != lens.max()):
+                raise ValueError("list-valued columns must have a constant length per row "
+                                 f"(found {int(lens.min())}..{int(lens.max())})")
         return flat.reshape(n, len(flat) // n)
     if col.null_count:
         raise ValueError("null values are not supported by the shuffling loader")
@@ -175,6 +207,9 @@ def load_table(index: DatasetIndex, row_start: int, row_stop: int,
             if width < 0:
                 width = arr.shape[1]
                 schema[n] = (code, width)
+            elif arr.ndim == 2 and arr.shape[1] != width:
+                raise ValueError(f"column {n}: rows of {arr.shape[1]} elements in "
+                                 f"{g.filename}, the dataset's first row group had {width}")
             buf = _ensure(n, width, arr.dtype)
             part = arr[lo:hi]
             if copy_fn is not None and part.flags.c_contiguous and part.nbytes >= (1 << 20):

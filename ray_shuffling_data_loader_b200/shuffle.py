@@ -29,38 +29,31 @@ from ray_shuffling_data_loader_b200.stats import TrialStatsCollector
 
 
 class BatchConsumer:
-    """
-    Interface for consumers of the shuffle outputs.
+    """Sink protocol of ``shuffle()`` - the four hooks the reference defines
+    (``shuffle.py:11-43``); method names and argument order are the contract, so a
+    consumer written for the reference plugs in unchanged.
+
+    * ``consume(rank, epoch, batches)``      trainer ``rank`` receives the epoch's reducer
+                                             chunks (``ShuffledChunk`` handles, possibly not
+                                             yet complete: call ``.wait()`` before reading)
+    * ``producer_done(rank, epoch)``         no more chunks will come for that trainer/epoch
+    * ``wait_until_ready(epoch)``            back-pressure: return when the shuffle of
+                                             ``epoch`` may start
+    * ``wait_until_all_epochs_done()``       return when everything handed out was consumed
     """
 
     def consume(self, rank, epoch, batches):
-        """
-        Consume the provided batches for the given trainer and epoch.
-        """
-        raise NotImplementedError(
-            "Derived classes must implement consume method.")
+        raise NotImplementedError(f"{type(self).__name__} must implement consume()")
 
     def producer_done(self, rank, epoch):
-        """
-        Signals to the consumer that we're done producing batches for the
-        given trainer and epoch.
-        """
-        raise NotImplementedError(
-            "Derived classes must implement producer_done method.")
+        raise NotImplementedError(f"{type(self).__name__} must implement producer_done()")
 
     def wait_until_ready(self, epoch):
-        """
-        Returns once the consumer is ready for this epoch to start.
-        """
-        raise NotImplementedError(
-            "Derived classes must implement wait_until_ready method.")
+        raise NotImplementedError(f"{type(self).__name__} must implement wait_until_ready()")
 
     def wait_until_all_epochs_done(self):
-        """
-        Returns once all batches for all epochs have been consumed.
-        """
         raise NotImplementedError(
-            "Derived classes must implement wait_until_done method.")
+            f"{type(self).__name__} must implement wait_until_all_epochs_done()")
 
 
 #
@@ -91,8 +84,11 @@ def shuffle(
         filenames (str): Paths to input Parquet files.
         batch_consumer (BatchConsumer): Consumer of shuffle outputs.
         num_epochs (int): Number of training epochs.
-        num_reducers (int): The number of shuffler reducers (destination
-            chunks with their own completion flag / ``consume`` item).
+        num_reducers (int): The number of shuffler reducers: destination
+            chunks handed to ``consume`` as separate items. On the GPU engine a
+            chunk's ``wait()`` returns as soon as the destination-chunk pass that
+            delivers it has completed (``chunk_passes`` engine option, K7), not
+            when the whole epoch has.
         num_trainers (int): Number of trainer workers.
         stats_collector(Optional[TrialStatsCollector]): Shuffle stats
             collector.

@@ -13,12 +13,17 @@ row packing happen inside the shuffle kernel's epilogue, so a batch is a
 ``[B, row_pitch]`` byte matrix already in HBM and every feature tensor is a
 strided zero-copy view of it; ``packed_features=True`` additionally exposes the
 single ``[B, F]`` matrix most models want.
+
+The data spec (which columns, their shapes and dtypes) is a small value object,
+``TensorSpec``; the packed-row layout is derived from it (``torch_layout``) and
+the same object drives both the device path (``packed_to_tensors``: views) and
+the host-side helper kept for API parity (``convert_to_tensor``).
 """
 from __future__ import annotations
 
 import functools
-from collections.abc import Iterable
-from typing import Any, Callable, List, Optional, Tuple
+from dataclasses import dataclass
+from typing import Any, Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -29,43 +34,109 @@ from ray_shuffling_data_loader_b200.ops import layout as L
 from ray_shuffling_data_loader_b200.runtime.chunks import field_tensor
 
 
+@dataclass(frozen=True)
+class ColumnSpec:
+    """One output tensor: source column, trailing shape (``None`` = ``(1,)``), dtype."""
+    name: Any
+    shape: Optional[Tuple[int, ...]]
+    dtype: torch.dtype
+
+    def trailing(self) -> Tuple[int, ...]:
+        return (1,) if self.shape is None else self.shape
+
+
+@dataclass(frozen=True)
+class TensorSpec:
+    """The feature/label contract of ``TorchShufflingDataset`` in one place.
+
+    Built by ``TensorSpec.build`` from the reference's six keyword arguments
+    (reference ``torch_dataset.py:144-201`` for the defaulting rules: scalars are
+    promoted to one-element lists, missing shapes mean ``(B, 1)``, missing dtypes
+    mean ``torch.float``); malformed specs raise ``ValueError``/``TypeError``
+    (they are user errors, and ``assert`` disappears under ``python -O``)."""
+    features: Tuple[ColumnSpec, ...]
+    label: Optional[ColumnSpec]
+
+    @staticmethod
+    def build(feature_columns=None, feature_shapes=None, feature_types=None,
+              label_column=None, label_shape=None, label_type=None) -> "TensorSpec":
+        names = list(feature_columns) if isinstance(feature_columns, (list, tuple)) \
+            else [feature_columns]
+        shapes = _broadcast_arg(feature_shapes, len(names), "feature_shapes")
+        dtypes = _broadcast_arg(feature_types, len(names), "feature_types")
+        feats = []
+        for name, shape, dtype in zip(names, shapes, dtypes):
+            if dtype is None:
+                dtype = torch.float
+            elif not isinstance(dtype, torch.dtype):
+                raise TypeError(f"feature_types entries must be torch.dtype, got {dtype!r}")
+            feats.append(ColumnSpec(name, _as_shape(shape), dtype))
+        label = None
+        if label_column is not None:
+            if label_type is not None and not isinstance(label_type, torch.dtype):
+                raise TypeError(f"label_type must be a torch.dtype, got {label_type!r}")
+            label = ColumnSpec(label_column, _as_shape(label_shape or None),
+                               label_type or torch.float)
+        return TensorSpec(tuple(feats), label)
+
+    @property
+    def columns(self) -> List[ColumnSpec]:
+        return list(self.features) + ([self.label] if self.label is not None else [])
+
+
+def _broadcast_arg(value, n: int, what: str) -> list:
+    """``None``/empty -> ``[None] * n``; a scalar -> one-element list; a list must
+    have one entry per feature column."""
+    if value is None or (isinstance(value, (list, tuple)) and len(value) == 0):
+        return [None] * n
+    # a bare shape tuple such as (3, 32, 32) for a single feature is one entry
+    if not isinstance(value, list):
+        value = [value]
+    if len(value) != n:
+        raise ValueError(f"{what} has {len(value)} entries for {n} feature columns")
+    return list(value)
+
+
+def _as_shape(shape) -> Optional[Tuple[int, ...]]:
+    if shape is None:
+        return None
+    if isinstance(shape, (int, np.integer)):
+        return (int(shape),)
+    return tuple(int(d) for d in shape)
+
+
 class TorchShufflingDataset(IterableDataset):
-    """
-    A PyTorch shuffling dataset that yields batches upon iteration.
+    """Per-epoch globally shuffled ``(features, label)`` tensor batches.
 
-    This dataset will kick off shuffling for max_concurrent_epochs epochs at
-    construction time.
+    Positional arguments and their order are the reference's
+    (``torch_dataset.py:45-59``) so existing call sites keep working:
 
-    Args:
-        filenames (str): Paths to input Parquet files.
-        num_epochs (int): Number of training epochs.
-        num_trainers (int): Number of trainer workers.
-        batch_size (int): Size of the batches that the iterator should yield.
-        rank (int): The worker rank of the current process.
-        drop_last (Optional[bool]): Whether to drop the last batch if it's
-            incomplete (smaller than batch_size). Default is False.
-        num_reducers (Optional[int]): The number of shuffler reducers.
-        max_concurrent_epochs (Optional[int]): The maximum number of epochs
-            whose shuffling stages should execute concurrently. Default is 2.
-        feature_columns (List[Any]): The feature columns' names.
-        feature_shapes (Optional[List[Any]]): The shape for each
-            feature. If provided, it should match the size of feature_columns.
-        feature_types (Optional[List[torch.dtype]]): The data type for each
-            feature. If provided, it should match the size of feature_columns.
-        label_column (Any): The label column name.
-        label_shape (Optional[int]): The shape for the label data.
-        label_type (Optional[torch.dtype]): The data type for the label data.
-        packed_features (bool): yield ``(features[B, F], label)`` with one
-            matrix instead of a list of ``(B, 1)`` views (needs a single
-            feature dtype). Extension; default False = reference contract.
-        row_align (int): opt-in padding of the packed row pitch to a multiple
-            of this power of two (e.g. 128 = one L2 line); see
-            ``ops/layout.py::build_layout``.
-        fp8_block_scale (bool): with ``feature_types`` all
-            ``torch.float8_e4m3fn``, emit MX-style block-scaled fp8 (one UE8M0
-            scale per 32 features, see ``ops/fp8.py``); the batch then yields
-            ``((payload, scales), label)`` in packed mode.
-        seed, backend, **engine_options: see ``ShufflingDataset``.
+    ``filenames``              input Parquet files (their concatenation is the table)
+    ``num_epochs``             epochs that will be iterated
+    ``num_trainers``           data-parallel consumers; each gets a disjoint 1/T of every epoch
+    ``batch_size``             rows per yielded batch (the last one may be short)
+    ``rank``                   which trainer this process is
+    ``drop_last``              skip the short final batch
+    ``num_reducers``           destination chunks per epoch with their own completion flag
+    ``max_concurrent_epochs``  epoch ring depth: how many shuffles may be in flight
+    ``feature_columns`` / ``feature_shapes`` / ``feature_types``
+                               one output tensor per column: ``(B, 1)`` or ``(B, *shape)``,
+                               dtype default ``torch.float`` (cast inside the shuffle kernel)
+    ``label_column`` / ``label_shape`` / ``label_type``
+                               the label tensor, ``(B, 1)`` or ``(B, label_shape)``
+
+    The first ``max_concurrent_epochs`` shuffles start in the constructor.
+
+    Keyword-only extensions:
+
+    ``packed_features``  yield one ``[B, F]`` matrix instead of F ``(B, 1)`` views
+                         (needs a single feature dtype)
+    ``row_align``        pad the packed row pitch to a multiple of this power of two
+                         (128 = one L2 line; see ``ops/layout.py::build_layout``)
+    ``fp8_block_scale``  with all-``float8_e4m3fn`` features: MX-style block scaling (one
+                         UE8M0 scale per 32 features, ``ops/fp8.py``); packed mode then
+                         yields ``((payload, scales), label)``
+    ``seed``, ``backend``, engine options: see ``ShufflingDataset``.
     """
 
     def __init__(self,
@@ -89,9 +160,8 @@ class TorchShufflingDataset(IterableDataset):
                  row_align: int = 0,
                  **dataset_options):
         super().__init__()
-        spec = _normalize_torch_data_spec(feature_columns, feature_shapes,
-                                          feature_types, label_column,
-                                          label_shape, label_type)
+        spec = TensorSpec.build(feature_columns, feature_shapes, feature_types,
+                                label_column, label_shape, label_type)
         self._spec = spec
         self._packed_features = packed_features
         self._fp8_block_scale = fp8_block_scale
@@ -119,15 +189,9 @@ class TorchShufflingDataset(IterableDataset):
         return self._ds
 
     def set_epoch(self, epoch):
-        """
-        Set the current training epoch. This should be called before
-        constructing the iterator on this dataset (e.g. before the
-        enumerate(train_loader) call).
-
-        Args:
-            epoch (int) The epoch number for the training epoch that is about
-                to start.
-        """
+        """Select the epoch the next ``iter()`` will read. Mandatory before every
+        pass and the value must change between passes (``ValueError`` otherwise),
+        exactly like the reference (``torch_dataset.py:78-88``)."""
         self._ds.set_epoch(epoch)
 
     def state_dict(self):
@@ -148,7 +212,10 @@ class TorchShufflingDataset(IterableDataset):
         cache = {}      # id(epoch buffer) -> (features, label) views of the WHOLE buffer
         for item in iter(self._ds):
             if isinstance(item, BatchSpan) and hasattr(item.buffer.data, "_offset"):
-                item = item.packed()      # chunk shipped from another process
+                # chunk shipped from the owning process (this rank only connected
+                # to its queue): the pickled chunk carries the layout with it
+                self._layout = item.buffer.layout
+                item = item.packed()
             if isinstance(item, BatchSpan):
                 buf = item.buffer
                 views = cache.get(id(buf))
@@ -186,7 +253,7 @@ class TorchShufflingDataset(IterableDataset):
                                     self._packed_features)
 
 
-def torch_layout(schema, spec, fp8_block_scale: bool = False, row_align: int = 0,
+def torch_layout(schema, spec: TensorSpec, fp8_block_scale: bool = False, row_align: int = 0,
                  reorder: bool = False) -> L.RowLayout:
     """Row layout for a Torch data spec: features in the given order, then the
     label; each source column is cast to its requested dtype. With ``reorder``
@@ -194,31 +261,25 @@ def torch_layout(schema, spec, fp8_block_scale: bool = False, row_align: int = 0
     class of columns the TMA scatter kernel can take in one launch is stored
     first - e.g. an int64 id in front of 40 float features no longer sends the
     whole row to the generic kernel."""
-    (feature_columns, feature_shapes, feature_types, label_column, label_shape,
-     label_type) = spec
     cols = []
-    for name, dtype in list(zip(feature_columns, feature_types)) + [(label_column, label_type)]:
-        if name is None:
-            continue
-        if name not in schema:
-            raise KeyError(f"column {name!r} not found in the Parquet schema "
+    for c in spec.columns:
+        if c.name not in schema:
+            raise KeyError(f"column {c.name!r} not found in the Parquet schema "
                            f"{list(schema)}")
-        src_code, width = schema[name]
-        cols.append((name, src_code, L.code_from_torch(dtype), max(1, width)))
+        src_code, width = schema[c.name]
+        cols.append((c.name, src_code, L.code_from_torch(c.dtype), max(1, width)))
     if reorder and not fp8_block_scale and len({c[0] for c in cols}) == len(cols):
         cols = [cols[i] for i in L.tma_friendly_order(cols)]
     return L.build_layout(cols, fp8_block_scale=fp8_block_scale, row_align=row_align)
 
 
-def packed_to_tensors(packed: torch.Tensor, layout: L.RowLayout, spec,
+def packed_to_tensors(packed: torch.Tensor, layout: L.RowLayout, spec: TensorSpec,
                       packed_features: bool = False):
     """``uint8[B, pitch]`` -> ``(features, label)`` views (no copies)."""
-    (feature_columns, feature_shapes, feature_types, label_column, label_shape,
-     label_type) = spec
     pitch = layout.row_pitch
     if packed_features:
-        first = layout.field(feature_columns[0])
-        last = layout.field(feature_columns[-1])
+        first = layout.field(spec.features[0].name)
+        last = layout.field(spec.features[-1].name)
         code = first.dst_code
         nelem = (last.offset + last.dst_bytes - first.offset) // L.itemsize(code)
         whole = L.Field("features", first.src_code, code, first.offset, nelem)
@@ -229,167 +290,115 @@ def packed_to_tensors(packed: torch.Tensor, layout: L.RowLayout, spec,
             features = (features, scales)
     else:
         features = []
-        for col, shape in zip(feature_columns, feature_shapes):
-            t = field_tensor(packed, layout.field(col), pitch)
-            if shape is not None:
-                t = t.reshape(*(-1, *shape))
+        for c in spec.features:
+            t = field_tensor(packed, layout.field(c.name), pitch)
+            if c.shape is not None:
+                t = t.reshape(-1, *c.shape)
             features.append(t)
-    if label_column is None:
+    if spec.label is None:
         return features, None
-    label = field_tensor(packed, layout.field(label_column), pitch)
-    if label_shape:
-        label = label.reshape(-1, label_shape)
+    label = field_tensor(packed, layout.field(spec.label.name), pitch)
+    if spec.label.shape is not None:
+        label = label.reshape(-1, *spec.label.shape)
     return features, label
 
 
-def dataframe_to_tensor_factory(
-        feature_columns: List[Any] = None,
-        feature_shapes: Optional[List[Any]] = None,
-        feature_types: Optional[List[torch.dtype]] = None,
-        label_column: Any = None,
-        label_shape: Optional[int] = None,
-        label_type: Optional[torch.dtype] = None,
-) -> Callable:
-    """
-    Returns a Pandas DataFrame --> PyTorch Tensor converter, using the
-    provided data spec to do the conversion (kept for users who iterate
-    ``ShufflingDataset(output="pandas")`` themselves; the fused kernel path
-    never builds a DataFrame).
-    """
-    spec = _normalize_torch_data_spec(feature_columns, feature_shapes,
-                                      feature_types, label_column, label_shape,
-                                      label_type)
-    return functools.partial(
-        convert_to_tensor,
-        feature_columns=spec[0],
-        feature_shapes=spec[1],
-        feature_types=spec[2],
-        label_column=spec[3],
-        label_shape=spec[4],
-        label_type=spec[5])
+# ---------------------------------------------------------------------------
+# host-side DataFrame -> tensors (API parity with the reference's helpers)
+# ---------------------------------------------------------------------------
+
+def _cells_to_array(values: np.ndarray, column) -> np.ndarray:
+    """Column values -> one dense ndarray. Object columns (what pandas gives for
+    Parquet list columns: one ndarray / list / tuple per row) are stacked."""
+    if values.dtype != object:
+        return values
+    if len(values) == 0:
+        return np.empty((0,), dtype=np.float32)
+    probe = values[0]
+    if not isinstance(probe, (np.ndarray, list, tuple)):
+        raise TypeError(f"column {column!r} holds {type(probe).__name__} cells; only numeric "
+                        "columns and ndarray/list/tuple cells of equal length are supported")
+    return np.stack([np.asarray(v) for v in values])
 
 
-def _normalize_torch_data_spec(
-        feature_columns: List[Any] = None,
-        feature_shapes: Optional[List[Any]] = None,
-        feature_types: Optional[List[torch.dtype]] = None,
-        label_column: Any = None,
-        label_shape: Optional[int] = None,
-        label_type: Optional[torch.dtype] = None):
-    """
-    Normalize the provided Torch data spec, returning sensible defaults for
-    unspecified parameters (same rules as reference torch_dataset.py:144-201).
-    """
-    # Convert to list for convenience.
-    if not isinstance(feature_columns, list):
-        feature_columns = [feature_columns]
-
-    if feature_shapes:
-        if not isinstance(feature_shapes, list):
-            feature_shapes = [feature_shapes]
-        assert len(feature_columns) == len(feature_shapes), \
-            "The feature_shapes size must match the feature_columns"
-        feature_shapes = [
-            s if (s is None or isinstance(s, Iterable)) else [s]
-            for s in feature_shapes]
-    else:
-        feature_shapes = [None] * len(feature_columns)
-
-    if feature_types:
-        if not isinstance(feature_types, list):
-            feature_types = [feature_types]
-        assert len(feature_columns) == len(feature_types), \
-            "The feature_types size must match the feature_columns"
-        assert all(isinstance(dtype, torch.dtype) for dtype in feature_types), \
-            "All value in feature_types should be torch.dtype instance"
-    else:
-        feature_types = [torch.float] * len(feature_columns)
-
-    if not label_type:
-        label_type = torch.float
-
-    return (feature_columns, feature_shapes, feature_types, label_column,
-            label_shape, label_type)
+def _to_tensor(df, c: ColumnSpec) -> torch.Tensor:
+    arr = _cells_to_array(df[c.name].to_numpy(), c.name)
+    if not (arr.flags.c_contiguous and arr.flags.writeable):
+        arr = np.array(arr, order="C")
+    t = torch.from_numpy(arr).to(c.dtype)
+    # same result shapes as the device path (``packed_to_tensors``): a scalar
+    # column is (B, 1), a list column without an explicit shape is (B, width)
+    return t.reshape(len(arr), -1) if c.shape is None else t.reshape(len(arr), *c.shape)
 
 
-def convert_to_tensor(df, feature_columns: List[Any],
-                      feature_shapes: List[Any],
-                      feature_types: List[torch.dtype], label_column: Any,
-                      label_shape: Optional[int], label_type: torch.dtype):
-    """Host-side DataFrame -> tensors conversion (reference semantics, fixed
-    for numpy >= 1.24 where ``np.object`` no longer exists)."""
-    feature_tensor = []
-    for col, shape, dtype in zip(feature_columns, feature_shapes,
-                                 feature_types):
-        column = df[col].values
-        if column.dtype == object:
-            if isinstance(column[0], np.ndarray):
-                column = np.stack(column)
-            elif isinstance(column[0], (list, tuple)):
-                column = list(column)
-            else:
-                raise Exception(
-                    f"Column {col}'s type: {type(column[0])} is not supported."
-                    " It must be numpy built in type or numpy object of "
-                    "(ndarray, list, tuple)")
-        t = torch.as_tensor(column, dtype=dtype)
-        if shape is not None:
-            t = t.view(*(-1, *shape))
-        else:
-            t = t.view(-1, 1)
-        feature_tensor.append(t)
-
-    label_df = df[label_column].values
-    label_tensor = torch.as_tensor(label_df, dtype=label_type)
-    if label_shape:
-        label_tensor = label_tensor.view(-1, label_shape)
-    else:
-        label_tensor = label_tensor.view(-1, 1)
-    return feature_tensor, label_tensor
+def convert_to_tensor(df, spec: Optional[TensorSpec] = None, **spec_kwargs):
+    """``DataFrame -> (features: List[Tensor], label: Tensor)`` on the host, for
+    callers that iterate ``ShufflingDataset(output="pandas")`` themselves (role of
+    reference ``torch_dataset.py:204-236``). Accepts a prebuilt ``TensorSpec`` or
+    the six spec keyword arguments. The GPU path never comes through here."""
+    if spec is None:
+        spec = TensorSpec.build(**spec_kwargs)
+    features = [_to_tensor(df, c) for c in spec.features]
+    label = _to_tensor(df, spec.label) if spec.label is not None else None
+    return features, label
 
 
-def _smoke_main():
-    """``python -m ray_shuffling_data_loader_b200.torch_dataset``: the
-    reference's smoke driver (``torch_dataset.py:239-309``)."""
-    import shutil
+def dataframe_to_tensor_factory(feature_columns=None, feature_shapes=None, feature_types=None,
+                                label_column=None, label_shape=None,
+                                label_type=None) -> Callable:
+    """A ``DataFrame -> tensors`` converter bound to one data spec (reference
+    ``torch_dataset.py:95-141``); the spec is validated once, here."""
+    spec = TensorSpec.build(feature_columns, feature_shapes, feature_types,
+                            label_column, label_shape, label_type)
+    return functools.partial(convert_to_tensor, spec=spec)
+
+
+def _smoke_main(argv: Optional[Sequence[str]] = None) -> int:
+    """``python -m ray_shuffling_data_loader_b200.torch_dataset``: end-to-end smoke
+    run on generated ``DATA_SPEC`` files (role of the reference's ``__main__``
+    block, ``torch_dataset.py:239-309``) - but it *checks* what it consumes: row
+    count per epoch, tensor shapes/dtypes, and that two epochs differ."""
+    import argparse
     import tempfile
-    from ray_shuffling_data_loader_b200.stats import human_readable_size
-    from ray_shuffling_data_loader_b200.data_generation import (generate_data,
-                                                                DATA_SPEC)
-    num_rows = 10**6
-    num_files = 10
-    data_dir = tempfile.mkdtemp()
-    filenames, num_bytes = generate_data(num_rows, num_files, 1, 0.0, data_dir)
-    print(f"Generated {len(filenames)} files containing {num_rows} rows, "
-          f"totalling {human_readable_size(num_bytes)}.")
-    num_epochs, num_trainers, batch_size, rank = 4, 1, 20000, 0
-    num_reducers, max_concurrent_epochs = 8, 2
-    feature_columns = list(DATA_SPEC.keys())
-    numpy_to_torch_dtype = {
-        np.bool_: torch.bool, np.uint8: torch.uint8, np.int8: torch.int8,
-        np.int16: torch.int16, np.int32: torch.int32, np.int64: torch.int64,
-        np.float16: torch.float16, np.float32: torch.float32,
-        np.float64: torch.float64}
-    feature_types = [numpy_to_torch_dtype[dtype] for _, _, dtype in DATA_SPEC.values()]
-    label_column = feature_columns.pop()
-    label_type = feature_types.pop()
-    print(f"Creating Torch shuffling dataset with {batch_size} batch size, "
-          f"{num_epochs} epochs, {num_reducers} reducers, and {num_trainers} "
-          "trainers.")
-    print(f"Should consume {num_rows // batch_size} batches.")
-    ds = TorchShufflingDataset(
-        filenames, num_epochs, num_trainers, batch_size, rank,
-        num_reducers=num_reducers, max_concurrent_epochs=max_concurrent_epochs,
-        feature_columns=feature_columns, feature_types=feature_types,
-        label_column=label_column, label_type=label_type)
-    for epoch in range(num_epochs):
-        ds.set_epoch(epoch)
-        for batch_idx, (data, targets) in enumerate(ds):
-            print(f"Epoch {epoch} - consuming batch {batch_idx}: "
-                  f"{len(data)} features, {len(targets)} samples")
-    print("Done consuming batches.")
-    shutil.rmtree(data_dir)
+    from ray_shuffling_data_loader_b200.data_generation import DATA_SPEC, generate_data
+    ap = argparse.ArgumentParser(description=_smoke_main.__doc__)
+    ap.add_argument("--num-rows", type=int, default=10**6)
+    ap.add_argument("--num-files", type=int, default=10)
+    ap.add_argument("--num-epochs", type=int, default=4)
+    ap.add_argument("--batch-size", type=int, default=20000)
+    ap.add_argument("--num-reducers", type=int, default=8)
+    ap.add_argument("--backend", default=None, choices=[None, "cpu", "cuda"])
+    a = ap.parse_args(argv)
+    to_torch = {np.dtype(np.int64): torch.int64, np.dtype(np.float64): torch.float64,
+                np.dtype(np.float32): torch.float32, np.dtype(np.int32): torch.int32}
+    *feature_columns, label_column = DATA_SPEC
+    dtypes = [to_torch[np.dtype(DATA_SPEC[c][2])] for c in DATA_SPEC]
+    with tempfile.TemporaryDirectory() as data_dir:
+        files, nbytes = generate_data(a.num_rows, a.num_files, 1, 0.0, data_dir)
+        print(f"{len(files)} files, {a.num_rows} rows, {nbytes / 1e6:.1f} MB decoded; "
+              f"{a.num_epochs} epochs of {-(-a.num_rows // a.batch_size)} batches")
+        ds = TorchShufflingDataset(
+            files, a.num_epochs, 1, a.batch_size, 0, num_reducers=a.num_reducers,
+            feature_columns=feature_columns, feature_types=dtypes[:-1],
+            label_column=label_column, label_type=dtypes[-1], backend=a.backend)
+        first_of_epoch = []
+        for epoch in range(a.num_epochs):
+            ds.set_epoch(epoch)
+            rows = 0
+            for i, (features, label) in enumerate(ds):
+                if i == 0:
+                    first_of_epoch.append(features[0][:8, 0].clone())
+                if len(features) != len(feature_columns) or label.shape[1] != 1:
+                    raise AssertionError("tensor contract violated")
+                rows += label.shape[0]
+            if rows != a.num_rows:
+                raise AssertionError(f"epoch {epoch}: {rows} rows, expected {a.num_rows}")
+            print(f"epoch {epoch}: {rows} rows in {i + 1} batches")
+        if a.num_epochs > 1 and all(torch.equal(first_of_epoch[0], t) for t in first_of_epoch[1:]):
+            raise AssertionError("every epoch started with the same rows: not shuffled")
+    print("ok")
+    return 0
 
 
 if __name__ == "__main__":
-    _smoke_main()
+    raise SystemExit(_smoke_main())

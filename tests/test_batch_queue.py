@@ -2,6 +2,7 @@
 (ray_shuffling_data_loader/tests/test_batch_queue.py) on the Ray-free queue,
 plus the epoch-window back-pressure and by-name connect the reference never tested."""
 import asyncio
+import os
 import threading
 import time
 
@@ -281,3 +282,33 @@ def test_connect_retries_then_fails(tmp_path, monkeypatch):
     with pytest.raises(ValueError, match="Unable to connect"):
         connect_queue_actor("nobody-home", num_retries=3, initial_backoff_s=0.01)
     assert time.monotonic() - t0 >= 0.01 + 0.02 + 0.04 - 1e-3   # exponential back-off
+
+
+def test_queue_dir_is_private_and_secret_is_not_the_name(tmp_path, monkeypatch):
+    """the socket directory must be 0700 and ours, and the handshake key
+    must come from a random 0600 secret, not from the public queue name."""
+    import stat
+    from ray_shuffling_data_loader_b200 import batch_queue as bq
+    d = tmp_path / "qdir"
+    d.mkdir(mode=0o755)
+    monkeypatch.setenv("RSDL_B200_QUEUE_DIR", str(d))
+    k1 = bq._authkey("some-queue")
+    assert stat.S_IMODE(os.stat(d).st_mode) == 0o700
+    sec = d / "secret"
+    assert sec.exists() and stat.S_IMODE(os.stat(sec).st_mode) == 0o600
+    assert bq._authkey("some-queue") == k1 and bq._authkey("other") != k1
+    import hashlib
+    assert k1 != hashlib.sha256(b"rsdl-b200:some-queue").digest()
+    # a directory owned by somebody else is refused (simulated through os.stat)
+    real_stat = os.stat
+
+    def fake_stat(path, *a, **kw):
+        st = real_stat(path, *a, **kw)
+        if str(path) == str(d):
+            vals = list(st)
+            vals[4] = st.st_uid + 1
+            return os.stat_result(vals)
+        return st
+    monkeypatch.setattr(bq.os, "stat", fake_stat)
+    with pytest.raises(PermissionError):
+        bq._socket_path("some-queue")

@@ -291,3 +291,126 @@ def test_shuffle_api_with_custom_consumer_and_stats(small_dataset, tmp_path):
     assert len(epoch_csv.columns) == 31 and len(epoch_csv) == num_epochs
     assert len(cons_csv.columns) == 10
     assert abs(trial_csv["row_throughput"][0] - num_epochs * n / duration) < 1e-6
+
+
+# ---------------------------------------------------------------------------
+# round-2 additions
+# ---------------------------------------------------------------------------
+
+def test_pandas_written_list_column(tmp_path):
+    """Parquet written by pandas from ndarray-valued cells is a plain
+    ``list<item>`` column (not fixed_size_list): its width comes from the footer at
+    scan time, so layouts built before any decode are correct."""
+    n = 240
+    img = np.arange(n * 6, dtype=np.float32).reshape(n, 6)
+    files = []
+    for i, sl in enumerate([slice(0, 100), slice(100, 240)]):
+        df = pd.DataFrame({"key": np.arange(n)[sl], "img": list(img[sl]),
+                           "y": np.arange(n, dtype=np.float64)[sl]})
+        fn = str(tmp_path / f"p{i}.parquet")
+        df.to_parquet(fn)
+        files.append(fn)
+    from ray_shuffling_data_loader_b200.runtime import ingest
+    assert ingest.scan_files(files).schema["img"][1] == 6
+    for native in (True, False):
+        ds = TorchShufflingDataset(files, 1, 1, 64, 0, num_reducers=2, feature_columns=["img"],
+                                   feature_shapes=[(2, 3)], label_column="y", seed=3,
+                                   backend="cpu", queue_name=f"plist{native}", native=native)
+        ds.set_epoch(0)
+        ys = []
+        for (e,), y in ds:
+            assert e.shape[1:] == (2, 3)
+            assert torch.equal(e.reshape(-1, 6)[:, 0], y[:, 0] * 6)
+            ys.append(y[:, 0])
+        assert sorted(torch.cat(ys).tolist()) == list(range(n))
+    # plain dataset: DataFrame with ndarray cells, like pandas reading the file
+    ds2 = ShufflingDataset(files, 1, 1, 240, 0, num_reducers=1, seed=0, backend="cpu",
+                           queue_name="plist-df")
+    ds2.set_epoch(0)
+    df = next(iter(ds2))
+    assert df["img"].iloc[0].shape == (6,)
+
+
+def test_ragged_list_column_is_rejected(tmp_path):
+    df = pd.DataFrame({"key": np.arange(4), "v": [np.zeros(2, np.float32), np.zeros(3, np.float32),
+                                                  np.zeros(2, np.float32), np.zeros(1, np.float32)]})
+    fn = str(tmp_path / "ragged.parquet")
+    df.to_parquet(fn)
+    ds = ShufflingDataset([fn], 1, 1, 4, 0, num_reducers=1, seed=0, backend="cpu",
+                          queue_name="ragged")
+    ds.set_epoch(0)
+    with pytest.raises(Exception, match="constant length|same length|shuffle driver"):
+        list(ds)
+
+
+def _torch_rank1_child(qdir, files, out_path):
+    import os
+    os.environ["RSDL_B200_QUEUE_DIR"] = qdir
+    import torch
+    from ray_shuffling_data_loader_b200 import TorchShufflingDataset
+    ds = TorchShufflingDataset(files, 2, 2, 500, 1, num_reducers=4,
+                               feature_columns=["key", "embeddings_name0"],
+                               feature_types=[torch.int64, torch.float32],
+                               label_column="labels", backend="cpu", queue_name="torch-2rank")
+    keys = []
+    for epoch in range(2):
+        ds.set_epoch(epoch)
+        for (k, e), y in ds:
+            assert k.dtype == torch.int64 and e.shape[1] == 1 and y.shape[1] == 1
+            keys.append(k[:, 0].clone())
+    torch.save(torch.cat(keys), out_path)
+
+
+def test_torch_dataset_connecting_rank_other_process(small_dataset, tmp_path, monkeypatch):
+    """The reference's canonical launch: rank 0 owns queue + shuffle, rank 1 (another
+    process, no torch.distributed) connects by name and gets tensors (used
+    to raise 'needs the layout of the owning process' and hang rank 0)."""
+    import multiprocessing as mp
+    files, n = small_dataset
+    monkeypatch.setenv("RSDL_B200_QUEUE_DIR", str(tmp_path))
+    out = str(tmp_path / "rank1.pt")
+    ds = TorchShufflingDataset(files, 2, 2, 500, 0, num_reducers=4,
+                               feature_columns=["key", "embeddings_name0"],
+                               feature_types=[torch.int64, torch.float32],
+                               label_column="labels", seed=5, backend="cpu",
+                               queue_name="torch-2rank")
+    p = mp.get_context("spawn").Process(target=_torch_rank1_child,
+                                        args=(str(tmp_path), files, out))
+    p.start()
+    mine = []
+    for epoch in range(2):
+        ds.set_epoch(epoch)
+        for (k, e), y in ds:
+            mine.append(k[:, 0].clone())
+    p.join(timeout=120)
+    assert p.exitcode == 0
+    theirs = torch.load(out)
+    both = torch.cat(mine + [theirs]).tolist()
+    assert sorted(both) == sorted(list(range(n)) * 2)
+
+
+def test_tensor_spec_and_host_converter():
+    from ray_shuffling_data_loader_b200.torch_dataset import (TensorSpec, convert_to_tensor,
+                                                              dataframe_to_tensor_factory)
+    spec = TensorSpec.build(["a", "img"], [None, (2, 2)], None, "y", None, torch.int64)
+    assert spec.features[0].dtype == torch.float and spec.features[1].shape == (2, 2)
+    assert spec.label.dtype == torch.int64 and spec.label.trailing() == (1,)
+    assert TensorSpec.build("a", None, None, "y").features[0].name == "a"     # scalar promotion
+    with pytest.raises(ValueError):
+        TensorSpec.build(["a", "b"], [None], None, "y")
+    with pytest.raises(TypeError):
+        TensorSpec.build(["a"], None, [np.float32], "y")
+    df = pd.DataFrame({"a": np.arange(5, dtype=np.int64),
+                       "img": [np.full(4, i, dtype=np.float32) for i in range(5)],
+                       "t": [(i, i) for i in range(5)],
+                       "y": np.arange(5, dtype=np.float64)})
+    feats, label = convert_to_tensor(df, spec)
+    assert feats[0].shape == (5, 1) and feats[0].dtype == torch.float32
+    assert feats[1].shape == (5, 2, 2) and float(feats[1][3, 1, 1]) == 3.0
+    assert label.dtype == torch.int64 and label.shape == (5, 1)
+    conv = dataframe_to_tensor_factory(["t"], None, [torch.int32], "y", 1)
+    (t,), y = conv(df)
+    assert t.shape == (5, 2) and t.dtype == torch.int32 and y.shape == (5, 1)
+    with pytest.raises(TypeError):
+        convert_to_tensor(pd.DataFrame({"s": ["x", "y"], "y": [0.0, 1.0]}),
+                          feature_columns=["s"], label_column="y")

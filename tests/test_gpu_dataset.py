@@ -129,3 +129,55 @@ def test_window_backpressure_many_epochs(float_dataset):
     for epoch in range(7):
         keys = np.concatenate([out[0][epoch], out[1][epoch]])
         assert np.array_equal(np.sort(keys), np.arange(n)), epoch
+
+
+def test_resume_with_start_epoch_beyond_window(float_dataset):
+    """a fresh process resuming at start_epoch >= max_concurrent_epochs
+    must not wait on consumed flags nobody will ever write (it used to sit in the
+    slot-reuse gate for flag_timeout_s). Resumed batches equal the uninterrupted run's."""
+    import time
+    files, n = float_dataset
+    cols = [f"f{i}" for i in range(15)]
+    kw = dict(num_reducers=2, feature_columns=cols, label_column="labels", seed=77,
+              packed_features=True, max_concurrent_epochs=2)
+    full = TorchShufflingDataset(files, 6, 1, 700, 0, queue_name="res-a", **kw)
+    want = {}
+    for epoch in range(6):
+        full.set_epoch(epoch)
+        want[epoch] = [f.clone() for f, _ in full]
+    state = None
+    full.dataset.close()
+    for mode in ("stream", "host"):
+        t0 = time.monotonic()
+        ds = TorchShufflingDataset(files, 6, 1, 700, 0, queue_name=f"res-{mode}", start_epoch=3,
+                                   backpressure=mode, flag_timeout_s=20.0, **kw)
+        ds.load_state_dict({"seed": 77, "epoch": 3, "batches_consumed": 2, "batch_size": 700})
+        for epoch in range(3, 6):
+            ds.set_epoch(epoch)
+            got = [f.clone() for f, _ in ds]
+            ref = want[epoch][2:] if epoch == 3 else want[epoch]
+            assert len(got) == len(ref)
+            assert all(torch.equal(a, b) for a, b in zip(got, ref)), (mode, epoch)
+        ds.dataset.engine.check_error()
+        assert time.monotonic() - t0 < 15.0, "resume sat in the back-pressure gate"
+        ds.dataset.close()
+
+
+def test_pandas_list_column_cuda(tmp_path):
+    """plain list<item> Parquet column (pandas ndarray cells) through the GPU path."""
+    import pandas as pd
+    n = 3000
+    img = np.arange(n * 32, dtype=np.float32).reshape(n, 32)
+    fn = str(tmp_path / "pl.parquet")
+    pd.DataFrame({"img": list(img), "y": np.arange(n, dtype=np.float64)}).to_parquet(fn)
+    ds = TorchShufflingDataset([fn], 1, 1, 512, 0, num_reducers=2, feature_columns=["img"],
+                               feature_shapes=[(4, 8)], label_column="y", seed=1,
+                               queue_name="plist-gpu")
+    ds.set_epoch(0)
+    ys = []
+    for (e,), y in ds:
+        assert e.is_cuda and e.shape[1:] == (4, 8)
+        assert torch.equal(e.reshape(-1, 32)[:, 0], y[:, 0] * 32)
+        ys.append(y[:, 0])
+    assert sorted(torch.cat(ys).tolist()) == list(range(n))
+    ds.dataset.close()

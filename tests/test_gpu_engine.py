@@ -298,21 +298,21 @@ def test_stream_wait_mode(tmp_path_factory):
         dev.close(); cpu.close()
 
 
-@pytest.mark.parametrize("sched", ["0", "1"])
-def test_producer_schedules_agree(tmp_path_factory, small_dataset, monkeypatch, sched):
+@pytest.mark.parametrize("sched", [0, 1])
+def test_producer_schedules_agree(tmp_path_factory, small_dataset, sched):
     """Both producer schedules of the TMA kernel (loader warps + tile-per-warp
     index vs cooperative index warps that also load) must give the golden bytes,
     for 4-byte and 8-byte sources, single- and multi-panel tables."""
-    monkeypatch.setenv("RSDL_SCHED", sched)
-    files = _float_files(tmp_path_factory, 150, name="sc" + sched)
+    files = _float_files(tmp_path_factory, 150, name=f"sc{sched}")
     cols = [f"f{i}" for i in range(149)] + ["labels"]
-    cpu, dev = _engines(files, _f32_layout(cols), 3)
+    cpu, dev = _engines(files, _f32_layout(cols), 3, sched=sched)
+    assert dev.sched == sched
     try:
         _compare_epochs(cpu, dev, epochs=(0, 1))
     finally:
         dev.close(); cpu.close()
     dfiles, _ = small_dataset
-    cpu, dev = _engines(dfiles, L.dataframe_layout, 2)
+    cpu, dev = _engines(dfiles, L.dataframe_layout, 2, sched=sched)
     assert dev.fast_mode == 3
     try:
         _compare_epochs(cpu, dev, epochs=(0, 1))
@@ -408,3 +408,84 @@ def test_wide_column_streaming_and_torch_api(tmp_path_factory):
             assert img.is_cuda and img.dtype == torch.bfloat16 and img.shape[1:] == (3, 16, 16)
             labels.append(y[:, 0].clone())
         assert sorted(torch.cat(labels).tolist()) == list(range(3001))
+
+
+# ---------------------------------------------------------------------------
+# K7: destination-chunk passes with their own completion flags
+# ---------------------------------------------------------------------------
+
+@pytest.mark.parametrize("passes", [2, 5])
+def test_chunk_passes_match_golden_all_kernels(tmp_path_factory, small_dataset, passes):
+    """Splitting an epoch's scatter into destination-chunk passes must not change a
+    byte: fast f32 (multi-panel), typed-64 copy, generic casts and the wide kernel."""
+    files = _float_files(tmp_path_factory, 70, name=f"cp{passes}")
+    cols = [f"f{i}" for i in range(69)] + ["labels"]
+    cpu, dev = _engines(files, _f32_layout(cols), 3, chunk_passes=passes)
+    assert dev.chunk_passes == passes and len(dev.pass_bounds) == passes
+    try:
+        _compare_epochs(cpu, dev, epochs=(0, 1, 2, 3))
+        dev.check_error()
+    finally:
+        dev.close(); cpu.close()
+    dfiles, _ = small_dataset
+    cpu, dev = _engines(dfiles, L.dataframe_layout, 2, chunk_passes=passes)
+    try:
+        _compare_epochs(cpu, dev, epochs=(0, 1))
+    finally:
+        dev.close(); cpu.close()
+    cpu, dev = _engines(dfiles, L.dataframe_layout, 2, chunk_passes=passes, force_generic=True)
+    try:
+        _compare_epochs(cpu, dev, epochs=(0, 1))
+    finally:
+        dev.close(); cpu.close()
+
+
+def test_chunk0_consumable_while_scatter_still_running(tmp_path_factory):
+    """K7 (reference dataset.py:133-139: a trainer starts on the first finished
+    reducer output). With chunk passes, chunk 0's flag fires after the first pass:
+    a copy of chunk 0 enqueued behind ``chunk.wait()`` on the consumer stream
+    (a) holds the golden bytes and (b) finishes before the epoch's last pass does."""
+    from ray_shuffling_data_loader_b200.runtime.chunks import ShuffledChunk
+    C = _native()
+    files = _float_files(tmp_path_factory, 64, nrows=1_500_000, nfiles=4, name="ttfb")
+    cols = [f"f{i}" for i in range(63)] + ["labels"]
+    plan_reducers = 4
+    from ray_shuffling_data_loader_b200.runtime.cpu_engine import CpuShuffleEngine
+    from ray_shuffling_data_loader_b200.runtime.device_engine import DeviceShuffleEngine
+    plan_args = dict(num_trainers=1, num_reducers=plan_reducers, batch_size=4096, drop_last=False)
+    cpu = CpuShuffleEngine(files, plan_args, _f32_layout(cols), 9)
+    dev = DeviceShuffleEngine(files, plan_args, _f32_layout(cols), 9, chunk_passes=4,
+                              wait_mode="stream")
+    try:
+        want = cpu.start_epoch(0)[0]
+        want.wait(120)
+        dev._ensure_ingested(0)
+        torch.cuda.synchronize()
+        lead = []
+        for epoch in (0, 1):
+            buf = dev.start_epoch(epoch)[0]
+            stream = torch.cuda.current_stream().cuda_stream
+            chunks = [ShuffledChunk(buf, i, a, b)
+                      for i, (a, b) in enumerate(dev.plan.trainer_chunks(0))]
+            assert len(chunks) == 4
+            chunks[0].wait()                      # enqueues ONE wait kernel: pass 0's flags
+            snap = buf.data[chunks[0].row_start:chunks[0].row_stop].clone()
+            e_c0 = C.event_create(True)
+            C.event_record(e_c0, stream)
+            e_end = C.event_create(True)
+            C.event_record(e_end, dev.shuffle_stream)
+            torch.cuda.synchronize()
+            lead.append(C.event_elapsed_ms(e_c0, e_end))
+            if epoch == 0:
+                assert np.array_equal(snap.cpu().numpy(),
+                                      want.data[chunks[0].row_start:chunks[0].row_stop])
+            for c in chunks[1:]:
+                c.wait()
+            assert dev.first_pass_ms(epoch) is not None
+            assert dev.first_pass_ms(epoch) < 0.6 * dev.epoch_kernel_ms(epoch)
+            buf.release()
+        # chunk 0 (and its copy) was done while later passes were still running
+        assert max(lead) > 0.0, lead
+        dev.check_error()
+    finally:
+        dev.close(); cpu.close()

@@ -20,7 +20,7 @@ def _free_port():
 
 
 def _worker(rank, world, port, files, ncols, dst_code, fp8, exchange, resident, out_dir,
-            peer_alloc="symm"):
+            peer_alloc="symm", chunk_passes=None):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
                       WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     import torch
@@ -36,9 +36,12 @@ def _worker(rank, world, port, files, ncols, dst_code, fp8, exchange, resident, 
     def fn(schema):
         return L.build_layout([(c, schema[c][0], dst_code, 1) for c in cols],
                               fp8_block_scale=fp8)
-    plan_args = dict(num_trainers=world, num_reducers=world, batch_size=1000, drop_last=False)
+    plan_args = dict(num_trainers=world, num_reducers=world * (chunk_passes or 1),
+                     batch_size=1000, drop_last=False)
     gold = CpuShuffleEngine(files, plan_args, fn, 42)          # all trainers, one process
     opts = dict(exchange=exchange, resident=resident, peer_alloc=peer_alloc)
+    if chunk_passes:
+        opts["chunk_passes"] = chunk_passes
     if resident == "host":
         opts["stream_chunk_rows"] = 4096
     dev = DeviceShuffleEngine(files, plan_args, fn, 42, rank=rank, world=world, **opts)
@@ -47,6 +50,13 @@ def _worker(rank, world, port, files, ncols, dst_code, fp8, exchange, resident, 
         gb = gold.start_epoch(epoch)
         db = dev.start_epoch(epoch)
         gb[rank].wait(120)
+        if chunk_passes:
+            # K7: every chunk is complete (all sources, over NVLink) as soon as ITS
+            # pass's flags have fired - checked chunk by chunk, first to last
+            for a, b in dev.plan.trainer_chunks(rank):
+                db[rank].wait(120, row_stop=b)
+                part = db[rank].data[a:b].cpu().numpy()
+                ok = ok and np.array_equal(part, gb[rank].data[a:b])
         db[rank].wait(120)
         got = db[rank].data.cpu().numpy()
         ok = ok and np.array_equal(got, gb[rank].data)
@@ -69,16 +79,17 @@ def _files(tmp_path_factory, ncols, nrows=60_013):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("exchange,resident,dst,fp8,peer_alloc", [
-    ("p2p", "hbm", 7, False, "symm"), ("p2p", "host", 7, False, "symm"),
-    ("p2p", "hbm", 6, False, "symm"), ("p2p", "hbm", 9, True, "symm"),
-    ("p2p", "hbm", 7, False, "ipc"), ("nccl", "hbm", 7, False, "symm")])
+@pytest.mark.parametrize("exchange,resident,dst,fp8,peer_alloc,passes", [
+    ("p2p", "hbm", 7, False, "symm", None), ("p2p", "host", 7, False, "symm", None),
+    ("p2p", "hbm", 6, False, "symm", None), ("p2p", "hbm", 9, True, "symm", None),
+    ("p2p", "hbm", 7, False, "ipc", None), ("nccl", "hbm", 7, False, "symm", None),
+    ("p2p", "hbm", 7, False, "symm", 3)])
 def test_multi_gpu_matches_golden(tmp_path_factory, tmp_path, exchange, resident, dst, fp8,
-                                  peer_alloc):
+                                  peer_alloc, passes):
     import torch.multiprocessing as mp
     world = min(torch.cuda.device_count(), 8)
     files = _files(tmp_path_factory, 64)
     mp.spawn(_worker, args=(world, _free_port(), files, 64, dst, fp8, exchange, resident,
-                            str(tmp_path), peer_alloc), nprocs=world, join=True)
+                            str(tmp_path), peer_alloc, passes), nprocs=world, join=True)
     for r in range(world):
         assert open(tmp_path / f"ok_{r}").read() == "1", f"rank {r} mismatch"

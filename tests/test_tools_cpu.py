@@ -107,3 +107,15 @@ def test_native_numa_helpers():
         assert after <= before                            # never widens the mask
         assert n == 0 or n == len(after)
         os.sched_setaffinity(0, before)
+
+
+def test_bench_effective_counts_and_exactly_once():
+    import bench
+    # the driver's flags (--steps 20 --warmup 5) with 50 batches per epoch and window 2
+    assert bench.effective_counts(20, 5, 50, 2) == (2, 1)
+    assert bench.effective_counts(20, 5, 50, 2, min_timed_epochs=20) == (2, 20)
+    assert bench.effective_counts(200, 100, 50, 2) == (2, 4)
+    assert bench.effective_counts(120, 260, 50, 3) == (6, 3)
+    ok = bench.exactly_once([10.0, 10.0 + 1e-12], 10.0)
+    assert ok["ok"] and ok["epochs_checked"] == 2
+    assert not bench.exactly_once([10.0, 10.5], 10.0)["ok"]
