@@ -33,6 +33,7 @@ def _unavailable(why: str):
 
 def main(args):
     import bench
+    t_process = time.perf_counter()
     bench.claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -109,62 +110,84 @@ def main(args):
     dev = torch.device("cuda", torch.cuda.current_device())
     acc = torch.zeros(1, dtype=torch.float64, device=dev)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    h2d = [0]
+    counters = {"h2d": 0, "rows": 0, "steps": 0}
     checksum = [0.0]
-    state = {"it": None, "epoch": 0}
 
-    def next_batch():
-        while True:
-            if state["it"] is None:
-                ds.set_epoch(state["epoch"])
-                state["it"] = iter(ds)
-            try:
-                return next(state["it"])
-            except StopIteration:
-                state["it"] = None
-                state["epoch"] += 1
+    def consume_epoch(epoch):
+        """One whole epoch through the reference's public iterator, consumed the way
+        its own example does (examples/horovod/ray_torch_shuffle.py:202-207)."""
+        ds.set_epoch(epoch)
+        for data, target in ds:
+            # the reference example's H2D: pageable .cuda() of every tensor
+            data = [t.cuda() for t in data]
+            target = target.cuda()
+            counters["h2d"] += sum(t.numel() * t.element_size() for t in data) + \
+                target.numel() * target.element_size()
+            counters["rows"] += int(target.shape[0])
+            counters["steps"] += 1
+            # same sink as our arm: reduce every value of the batch, read it back
+            acc.add_(torch.stack([t.sum(dtype=torch.float64) for t in data]).sum()
+                     + target.sum(dtype=torch.float64))
+            checksum[0] = float(acc.item())
 
-    def step():
-        data, target = next_batch()
-        # the reference example's H2D: pageable .cuda() of every tensor
-        data = [t.cuda() for t in data]
-        target = target.cuda()
-        h2d[0] += sum(t.numel() * t.element_size() for t in data) + \
-            target.numel() * target.element_size()
-        # same sink as our arm: reduce every value of the batch, read it back
-        nonlocal_acc = torch.stack([t.sum(dtype=torch.float64) for t in data]).sum() \
-            + target.sum(dtype=torch.float64)
-        acc.add_(nonlocal_acc)
-        checksum[0] = float(acc.item())
+    def agree(x):
+        """max over ranks of a host float (so every rank takes the same decision)"""
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    for _ in range(warmup):
-        step()
+    # warm-up: whole epochs, each one timed - the last one is the fallback measurement
+    # if the time budget (the driver kills a run after ~870 s) leaves no room for more
+    last_warm = None
+    for e in range(warm_ep):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        c0 = dict(counters)
+        t0 = time.perf_counter()
+        consume_epoch(e)
+        torch.cuda.synchronize()
+        last_warm = {"wall": agree(time.perf_counter() - t0), "rows": counters["rows"] - c0["rows"],
+                     "steps": counters["steps"] - c0["steps"], "h2d": counters["h2d"] - c0["h2d"]}
+    elapsed = agree(time.perf_counter() - t_process)
+    room = args.time_budget_s - elapsed
+    fit = int(room // max(last_warm["wall"], 1e-3))
+    fallback = fit < 1
+    if not fallback:
+        timed_ep = max(1, min(timed_ep, fit))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     if sampler:
         sampler.start()
-    h2d[0] = 0
-    # like our arm: the clock starts BEFORE the first timed batch is fetched
-    wall0 = time.perf_counter()
-    ev0.record()
-    for _ in range(steps):
-        step()
-    ev1.record()
-    torch.cuda.synchronize()
-    wall = time.perf_counter() - wall0
-    h2d_bytes = h2d[0]
-    checksum = checksum[0]
+    if fallback:
+        measured = dict(last_warm)
+        measured["ms"] = last_warm["wall"] * 1e3
+        timed_ep = 1
+    else:
+        c0 = dict(counters)
+        wall0 = time.perf_counter()
+        ev0.record()
+        for e in range(warm_ep, warm_ep + timed_ep):
+            consume_epoch(e)
+        ev1.record()
+        torch.cuda.synchronize()
+        measured = {"wall": agree(time.perf_counter() - wall0), "ms": agree(ev0.elapsed_time(ev1)),
+                    "rows": counters["rows"] - c0["rows"], "steps": counters["steps"] - c0["steps"],
+                    "h2d": counters["h2d"] - c0["h2d"]}
     clocks = sampler.stop() if sampler else None
-    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
-    wall_t = torch.tensor([wall], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(measured["rows"]), float(measured["steps"]), float(measured["h2d"])],
+                       dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(wall_t, op=dist.ReduceOp.MAX)
-    ms, wall = float(ms.item()), float(wall_t.item())
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    rows_all, steps_all, h2d_all = (float(x) for x in tot.tolist())
+    wall, ms = measured["wall"], measured["ms"]
+    checksum = checksum[0]
     if rank == 0:
-        rows = steps * args.batch_size * world
-        value = rows / wall
+        steps = max(1, int(round(steps_all / world)))        # batches per trainer in the region
+        warmup = warm_ep * batches_per_epoch
+        value = rows_all / wall
         out = {
             "metric": bench.METRIC, "value": value, "unit": "rows/s", "n_gpus": world,
             "steps": steps, "warmup": warmup, "ms_per_step": wall * 1e3 / steps,
@@ -176,8 +199,10 @@ def main(args):
             "batches_per_epoch": batches_per_epoch,
             "config": bench.shape_config(args, world),
             "batches_per_sec": value / args.batch_size,
+            "timed_region": ("last warm-up epoch (time budget of %.0f s left no room)"
+                             % args.time_budget_s) if fallback else "whole epochs after warm-up",
             "e2e": {"value": value, "unit": "rows/s",
-                    "h2d_bytes_per_step": int(h2d_bytes / steps),
+                    "h2d_bytes_per_step": int(h2d_all / max(1.0, steps_all)),
                     "d2h_bytes_per_step": 8, "ms_per_step": wall * 1e3 / steps,
                     "device_ms_per_step": ms / steps},
             "gpu_launches": 0, "clocks": clocks, "checksum": checksum,

@@ -106,6 +106,9 @@ def parse_args():
     p.add_argument("--max-concurrent-epochs", type=int, default=2,
                    help="epoch window (BASELINE config 3 compares 1 vs 2)")
     p.add_argument("--skip-e2e", action="store_true")
+    p.add_argument("--time-budget-s", type=float, default=600.0,
+                   help="reference arm: shrink the timed region (whole epochs, >= 1) so the "
+                        "run ends within this many seconds of wall clock")
     p.add_argument("--keep-data", action="store_true")
     return p.parse_args()
 
@@ -298,12 +301,20 @@ def run_phase(ds, engine, torch, dist, world, warm_epochs, timed_epochs, d2h_eac
         dist.all_reduce(wall_t, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
     kernel_ms = [engine.epoch_kernel_ms(e) for e in range(warm_epochs + window, n_ep + window)]
-    kernel_ms = [k for k in kernel_ms if k]
+    kernel_ms = sorted(k for k in kernel_ms if k)
+    # the same statistic on every rank: an epoch is only as fast as the slowest source
+    med = torch.tensor([kernel_ms[len(kernel_ms) // 2] if kernel_ms else 0.0],
+                       dtype=torch.float64, device=dev)
+    per_rank = [med.clone() for _ in range(world)]
+    if world > 1:
+        dist.all_gather(per_rank, med)
+    kernel_ms_per_rank = [float(x.item()) for x in per_rank]
     return {"ms": float(ms.item()), "wall": float(wall_t.item()),
             "steps": steps_done[0] - warm_steps, "warm_steps": warm_steps,
             "launches": c1[0] - c0[0], "scatter_launches": c1[1] - c0[1],
             "h2d_bytes": c1[2] - c0[2], "epoch_sums": sums.cpu().tolist(),
-            "kernel_ms": kernel_ms, "checksum": checksum[0] if d2h_each_step else None}
+            "kernel_ms": kernel_ms, "kernel_ms_per_rank": kernel_ms_per_rank,
+            "checksum": checksum[0] if d2h_each_step else None}
 
 
 def expected_table_sum(engine, torch, dist, world):
@@ -450,7 +461,8 @@ def run_ours(args):
         # bytes the shuffle moves per epoch per GPU: read source once + write rows once
         epoch_bytes = args.rows_per_gpu * (src_row_bytes + row_pitch)
         kms = sorted(res["kernel_ms"])
-        kernel_ms = kms[len(kms) // 2] if kms else None         # median over the timed epochs
+        # median over the timed epochs, of the SLOWEST rank (that one sets the epoch time)
+        kernel_ms = max(res["kernel_ms_per_rank"]) or None
         egress = (args.rows_per_gpu * row_pitch * (world - 1) / world / (kernel_ms / 1e3) / 1e9
                   if kernel_ms and world > 1 else None)
         out = {
@@ -473,6 +485,7 @@ def run_ours(args):
             "ms_per_epoch": res["ms"] / timed_ep,
             "shuffle_kernel_ms_per_epoch": kernel_ms,
             "shuffle_kernel_ms_min_max": [kms[0], kms[-1]] if kms else None,
+            "shuffle_kernel_ms_per_rank": res["kernel_ms_per_rank"],
             "shuffle_kernel_gbps": (epoch_bytes / (kernel_ms / 1e3) / 1e9 if kernel_ms else None),
             "hbm_roofline_frac_of_measured": (
                 epoch_bytes / (kernel_ms / 1e3) / 1e9 / peaks["hbm_gbs"]

@@ -678,6 +678,11 @@ PYBIND11_MODULE(_C, m) {
     rsdl::launch_batch_sum_all_f32(as_ptr<const uint8_t>(packed), nbytes, as_ptr<double>(out),
                                    as_stream(stream));
   });
+  m.def("bulk_store_probe", [](uintptr_t dst, uint64_t slots, uint32_t row_bytes,
+                               uint64_t total_rows, int grid, uintptr_t stream) {
+    rsdl::launch_bulk_store_probe(as_ptr<uint8_t>(dst), slots, row_bytes, total_rows, grid,
+                                  as_stream(stream));
+  }, "rate probe: TMA bulk stores (smem -> global) of `row_bytes` rows to random slots");
   m.def("signal_flags", [](const std::vector<uintptr_t>& ptrs, uint32_t value, uintptr_t stream) {
     if (ptrs.size() > RSDL_MAX_TRAINERS) throw std::runtime_error("too many flag targets");
     FlagTargets t;

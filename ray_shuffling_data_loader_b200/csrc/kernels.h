@@ -92,6 +92,8 @@ void launch_batch_sum_f32(const uint8_t* packed, unsigned long long rows, uint32
                           uint32_t off, double* out, cudaStream_t stream);
 void launch_batch_sum_all_f32(const uint8_t* packed, unsigned long long nbytes, double* out,
                               cudaStream_t stream);
+void launch_bulk_store_probe(uint8_t* dst, unsigned long long slots, uint32_t row_bytes,
+                             unsigned long long total_rows, int grid, cudaStream_t stream);
 void launch_signal_flags(const FlagTargets& t, uint32_t value, cudaStream_t stream);
 void launch_wait_flags(const uint32_t* flags, uint32_t count, uint32_t value,
                        unsigned long long timeout_ns, uint32_t* error, cudaStream_t stream);

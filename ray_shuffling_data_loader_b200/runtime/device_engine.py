@@ -146,9 +146,17 @@ class DeviceShuffleEngine:
         self.exchange_pg = exchange_group if exchange_group is not None else process_group
         self.stats = stats_collector
         self.window = max(1, int(max_concurrent_epochs))
-        self.num_threads = num_threads or max(1, min(16, (os.cpu_count() or 2)))
-        if resident not in ("hbm", "host"):
-            raise ValueError("resident must be 'hbm' or 'host'")
+        # decode / staging threads: this rank's share of the CPUs it may run on
+        # (after NUMA binding), at most 32 - Parquet decode is the cold path's
+        # bottleneck and row groups decode independently
+        try:
+            avail = len(os.sched_getaffinity(0))
+        except AttributeError:
+            avail = os.cpu_count() or 2
+        share = avail // max(1, world) if not self.numa_cpus else avail // max(1, (world + 1) // 2)
+        self.num_threads = num_threads or max(2, min(32, share))
+        if resident not in ("hbm", "host", "disk"):
+            raise ValueError("resident must be 'hbm', 'host' or 'disk'")
         if exchange not in ("p2p", "nccl"):
             raise ValueError("exchange must be 'p2p' or 'nccl'")
         if wait_mode not in ("host", "stream"):
@@ -194,7 +202,7 @@ class DeviceShuffleEngine:
         max_chunks = max(self.plan.reducers_of_trainer(t) for t in range(self.plan.num_trainers))
         if chunk_passes is None:
             chunk_passes = min(4, max_chunks) if world > 1 else 1
-        if resident == "host" or exchange == "nccl":
+        if resident != "hbm" or exchange == "nccl":
             chunk_passes = 1
         self.chunk_passes = max(1, min(int(chunk_passes), 64, max(1, self.plan.max_trainer_rows)))
         from ray_shuffling_data_loader_b200.ops.plan import balanced_split
@@ -217,10 +225,19 @@ class DeviceShuffleEngine:
 
         lo, hi = self.plan.source_range(rank, world)
         self.src_lo, self.n_local = lo, hi - lo
-        self.chunk_rows = (self.n_local if resident == "hbm" else
-                           max(1, min(self.n_local or 1,
-                                      stream_chunk_rows or self.plan.batch_size)))
-        if resident == "host":
+        if resident == "disk":
+            # the streaming unit is a Parquet row group (re-decoded every epoch):
+            # staging buffers hold the largest one this rank owns
+            mine = [g for g in self.index.row_groups
+                    if g.global_start < hi and g.global_start + g.num_rows > lo and g.num_rows]
+            self._disk_groups = mine
+            self.chunk_rows = max([min(hi, g.global_start + g.num_rows) - max(lo, g.global_start)
+                                   for g in mine] or [1])
+        else:
+            self.chunk_rows = (self.n_local if resident == "hbm" else
+                               max(1, min(self.n_local or 1,
+                                          stream_chunk_rows or self.plan.batch_size)))
+        if resident != "hbm":
             self.chunk_rows = _align(self.chunk_rows, self.C.TILE_ROWS)
 
         prio_lo, prio_hi = self.C.stream_priority_range()
@@ -383,7 +400,7 @@ class DeviceShuffleEngine:
                 off += len(_pad(g.tobytes()))
             self.generic_fields_dev.append(run_ptrs)
         self.fast_kinds_dev = off           # per-column conversion kinds (mode 4)
-        if self.resident == "host":
+        if self.resident != "hbm":
             self.h2d_done = [C.event_create(False) for _ in range(self.num_src_bufs)]
             self.buf_free = [C.event_create(False) for _ in range(self.num_src_bufs)]
             self._buf_used = [False] * self.num_src_bufs
@@ -523,6 +540,13 @@ class DeviceShuffleEngine:
             C = self.C
             t0 = timeit.default_timer()
             nfiles = len(self.index.filenames)
+            if self.resident == "disk":
+                # nothing is kept: every epoch re-decodes its row groups (_stream_epoch_disk)
+                self._pinned = []
+                self._ingested = True
+                self.ingest_seconds = 0.0
+                self.decode_seconds = 0.0
+                return
             if self.stats is not None:
                 for _ in range(nfiles):
                     self.stats.map_start(epoch)
@@ -552,10 +576,32 @@ class DeviceShuffleEngine:
                 return host_block[off:off + nbytes].view(dt).reshape(shape)
 
             names = [f.name for f in self.src_fields]
+            # resident="hbm": every decoded column slice is handed to the copy engine
+            # the moment its row group is in pinned memory (decode || H2D), instead of
+            # copying whole columns after the last row group has been decoded.
+            by_name: Dict[str, List[int]] = {}
+            for i, f in enumerate(self.src_fields):
+                by_name.setdefault(f.name, []).append(i)
+            h2d_lock = threading.Lock()
+            dev_index = self.device_index
+
+            def stage(name, first_row, rows, colbuf):
+                C.set_device(dev_index)               # decode threads: device is per-thread
+                for i in by_name.get(name, ()):
+                    f = self.src_fields[i]
+                    isz = L.itemsize(f.src_code) * f.width
+                    with h2d_lock:
+                        C.memcpy_async(self.src_col_ptrs[0][i] + first_row * isz,
+                                       colbuf.ctypes.data + first_row * isz, rows * isz,
+                                       C.H2D, self.copy_stream)
+
+            t_dec = timeit.default_timer()
             table = ingest.load_table(self.index, self.src_lo, self.src_lo + self.n_local,
                                       columns=list(dict.fromkeys(names)),
                                       num_threads=self.num_threads, alloc=alloc,
-                                      copy_fn=self._host_copy)
+                                      copy_fn=self._host_copy,
+                                      on_slice=stage if self.resident == "hbm" else None)
+            self.decode_seconds = timeit.default_timer() - t_dec
             self.host_table = table
             self.host_cols = [table.columns[f.name] for f in self.src_fields]
             for f, col in zip(self.src_fields, self.host_cols):
@@ -563,10 +609,7 @@ class DeviceShuffleEngine:
                 if col.dtype != want:
                     raise TypeError(f"column {f.name}: decoded {col.dtype}, expected {want}")
             if self.resident == "hbm":
-                for ptr, col in zip(self.src_col_ptrs[0], self.host_cols):
-                    if col.nbytes:
-                        C.memcpy_async(ptr, col.ctypes.data, col.nbytes, C.H2D, self.copy_stream)
-                C.stream_synchronize(self.copy_stream)
+                C.stream_synchronize(self.copy_stream)     # the tail of the overlapped copies
                 # decoded host copy is no longer needed once resident in HBM
                 self.host_cols = None
                 self.host_table = None
@@ -707,6 +750,9 @@ class DeviceShuffleEngine:
                 if k == 0 and self.chunk_passes > 1:
                     ev_first = C.event_create(True)
                     C.event_record(ev_first, self.shuffle_stream)
+        elif self.resident == "disk":
+            self._stream_epoch_disk(key_words, dst, epoch)
+            self._signal_produced(slot, 0, epoch)
         else:
             self._stream_epoch(key_words, dst)
             self._signal_produced(slot, 0, epoch)
@@ -763,6 +809,103 @@ class DeviceShuffleEngine:
             self._buf_used[b] = True
             k += 1
 
+    def _stream_epoch_disk(self, key_words, dst, epoch: int):
+        """resident='disk' - tables larger than pinned host memory (the reference's
+        only mode: it re-reads Parquet every epoch, ``shuffle.py:151``). Row groups
+        are decoded by a bounded pool into a ring of pinned staging buffers
+        (``disk_prefetch`` + 2 of them, each one row group), copied to one of two
+        device staging buffers and scattered; decode of the next row groups, the
+        H2D of this one and the scatter of the previous one overlap. Host memory
+        in use is bounded by the ring, not by the table."""
+        from concurrent.futures import ThreadPoolExecutor
+        C = self.C
+        groups = self._disk_groups
+        if not groups:
+            return
+        if not hasattr(self, "_disk_ring"):
+            depth = max(2, min(self.num_threads, len(groups))) + 2
+            per_buf = sum(self.col_bytes)
+            self._disk_ring = []
+            for _ in range(depth):
+                arr, ptr = pinned_array(C, (per_buf,), np.uint8)
+                self._pinned.append(ptr)
+                self._disk_ring.append({"arr": arr, "ptr": ptr, "copied": C.event_create(False),
+                                        "used": False})
+            self._disk_pool = ThreadPoolExecutor(max_workers=depth - 2,
+                                                 thread_name_prefix="disk-decode")
+        ring = self._disk_ring
+        host_off, off = {}, 0           # a column's place inside a pinned staging slot
+        for f, nb in zip(self.src_fields, self.col_bytes):
+            host_off.setdefault(f.name, off)
+            off += nb
+        names = list(dict.fromkeys(f.name for f in self.src_fields))
+        lo_all, hi_all = self.src_lo, self.src_lo + self.n_local
+        stats = self.stats
+        if stats is not None:
+            for _ in range(len(self.index.filenames)):
+                stats.map_start(epoch)
+
+        def decode(g, slot):
+            """one row group -> pinned staging slot (columns at the device layout's offsets)"""
+            if slot["used"]:
+                C.event_synchronize(slot["copied"])        # its previous H2D has drained
+            lo, hi = max(lo_all, g.global_start), min(hi_all, g.global_start + g.num_rows)
+            offs = host_off
+
+            t0 = timeit.default_timer()
+            bufs = {}
+            for f in self.src_fields:
+                if f.name in bufs:
+                    continue
+                dt = np.dtype(L.numpy_storage_dtype(f.src_code))
+                n = (hi - lo) * max(1, f.width)
+                view = slot["arr"][offs[f.name]:offs[f.name] + n * dt.itemsize].view(dt)
+                bufs[f.name] = view if f.width == 1 else view.reshape(hi - lo, f.width)
+            table = ingest.load_table(self.index, lo, hi, columns=names, num_threads=1,
+                                      prealloc=bufs)
+            return lo, hi - lo, timeit.default_timer() - t0, (table.read_durations or [0.0])[0]
+
+        pending = []
+        depth = len(ring)
+        it = iter(enumerate(groups))
+
+        def submit_next():
+            nxt = next(it, None)
+            if nxt is None:
+                return
+            k, g = nxt
+            slot = ring[k % depth]
+            pending.append((slot, self._disk_pool.submit(decode, g, slot)))
+        for _ in range(depth - 2):
+            submit_next()
+        k = 0
+        read_times = []
+        while pending:
+            slot, fut = pending.pop(0)
+            row0, rows, total_s, read_s = fut.result()
+            read_times.append(read_s)
+            b = k % self.num_src_bufs
+            if self._buf_used[b]:
+                C.stream_wait_event(self.copy_stream, self.buf_free[b])
+            for i, f in enumerate(self.src_fields):
+                isz = L.itemsize(f.src_code) * f.width
+                C.memcpy_async(self.src_col_ptrs[b][i], slot["ptr"] + host_off[f.name],
+                               rows * isz, C.H2D, self.copy_stream)
+                self.h2d_bytes_enqueued += rows * isz
+            C.event_record(slot["copied"], self.copy_stream)
+            slot["used"] = True
+            C.event_record(self.h2d_done[b], self.copy_stream)
+            C.stream_wait_event(self.shuffle_stream, self.h2d_done[b])
+            self._launch_chunk(key_words, b, rows, row0, dst)
+            C.event_record(self.buf_free[b], self.shuffle_stream)
+            self._buf_used[b] = True
+            k += 1
+            submit_next()
+        if stats is not None:
+            nfiles = len(self.index.filenames)
+            for _ in range(nfiles):
+                stats.map_done(epoch, 0.0, float(np.mean(read_times or [0.0])))
+
     def _host_copy(self, dst: np.ndarray, src: np.ndarray):
         """Decoded Arrow buffer -> pinned staging on the C++ worker pool."""
         self.host_pool.parallel_memcpy(dst.ctypes.data, src.ctypes.data, src.nbytes)
@@ -795,7 +938,7 @@ class DeviceShuffleEngine:
             i = j
 
     def h2d_bytes_per_epoch(self) -> int:
-        if self.resident != "host":
+        if self.resident == "hbm":
             return 0
         return int(sum(self.n_local * L.itemsize(f.src_code) * f.width
                        for f in self.src_fields))
@@ -1028,9 +1171,13 @@ class DeviceShuffleEngine:
                 C.event_destroy(ev[1])
             self._events.clear()
             self._first_pass_events.clear()
-            if self.resident == "host":
+            if self.resident != "hbm":
                 for e in self.h2d_done + self.buf_free:
                     C.event_destroy(e)
+            if hasattr(self, "_disk_pool"):
+                self._disk_pool.shutdown(wait=True)
+                for slot in self._disk_ring:
+                    C.event_destroy(slot["copied"])
             for ptr in getattr(self, "_pinned", []):
                 C.pinned_free(ptr)
             self._pinned = []

@@ -154,7 +154,9 @@ def load_table(index: DatasetIndex, row_start: int, row_stop: int,
                num_threads: int = 8,
                alloc: Optional[Callable[[Tuple[int, ...], np.dtype], np.ndarray]] = None,
                on_read: Optional[Callable[[float, float], None]] = None,
-               copy_fn: Optional[Callable[[np.ndarray, np.ndarray], None]] = None) -> HostTable:
+               copy_fn: Optional[Callable[[np.ndarray, np.ndarray], None]] = None,
+               on_slice: Optional[Callable[[str, int, int, np.ndarray], None]] = None,
+               prealloc: Optional[Dict[str, np.ndarray]] = None) -> HostTable:
     """Decode global rows ``[row_start, row_stop)``.
 
     ``alloc(shape, dtype)`` supplies the destination buffers (pinned host
@@ -162,7 +164,13 @@ def load_table(index: DatasetIndex, row_start: int, row_stop: int,
     ``on_read(total_duration, read_duration)`` is invoked per row group (feeds
     the map-stage stats, the analogue of reference ``shuffle.py:147-167``).
     ``copy_fn(dst, src)`` copies a decoded contiguous column slice into its
-    (pinned) destination - the native runtime's GIL-free parallel memcpy."""
+    (pinned) destination - the native runtime's GIL-free parallel memcpy.
+    ``on_slice(name, first_row, rows, column_buffer)`` fires (on the decode thread)
+    as soon as rows ``[first_row, first_row + rows)`` of a column are in place - the
+    GPU engine enqueues that slice's H2D copy right there, so staging into HBM
+    overlaps the decode of the remaining row groups instead of following it.
+    ``prealloc`` supplies ready-made destination arrays per column (the disk-streaming
+    mode's pinned staging slots) instead of calling ``alloc``."""
     names = list(columns) if columns is not None else list(index.schema.keys())
     for n in names:
         if n not in index.schema:
@@ -172,7 +180,7 @@ def load_table(index: DatasetIndex, row_start: int, row_stop: int,
             if g.global_start < row_stop and g.global_start + g.num_rows > row_start
             and g.num_rows > 0]
     schema = {n: index.schema[n] for n in names}
-    bufs: Dict[str, np.ndarray] = {}
+    bufs: Dict[str, np.ndarray] = dict(prealloc) if prealloc else {}
     alloc = alloc or (lambda shape, dt: np.empty(shape, dtype=dt))
 
     alloc_lock = threading.Lock()
@@ -216,6 +224,8 @@ def load_table(index: DatasetIndex, row_start: int, row_stop: int,
                 copy_fn(buf[dst:dst + (hi - lo)], part)
             else:
                 buf[dst:dst + (hi - lo)] = part
+            if on_slice is not None and hi > lo:
+                on_slice(n, dst, hi - lo, buf)
         t2 = timeit.default_timer()
         return t2 - t0, t1 - t0
 

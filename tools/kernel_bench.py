@@ -59,11 +59,38 @@ def main():
     ap.add_argument("--sched", type=int, default=-1,
                     help="producer schedule: -1 auto, 0 loader warps, 1 cooperative")
     ap.add_argument("--tag", default="")
+    ap.add_argument("--bulk-store-probe", type=int, default=0, metavar="ROW_BYTES",
+                    help="instead of the scatter: rate of TMA bulk stores (smem -> global, "
+                         "UBLKCP.G.S) of ROW_BYTES rows to random slots (local, or --peer)")
     a = ap.parse_args()
     load_ext(a.ext)
     torch.cuda.set_device(0)
     _C.set_device(0)
     sm = _C.sm_count(0)
+    if a.bulk_store_probe:
+        rb = a.bulk_store_probe
+        total = 3_200_000_000 // rb
+        where = f"cuda:{a.peer}" if a.peer >= 0 else "cuda:0"
+        if a.peer >= 0:
+            _C.enable_peer_access(a.peer)
+        dst = torch.zeros(total * rb, dtype=torch.uint8, device=where)
+        torch.cuda.synchronize()
+        stream = torch.cuda.current_stream().cuda_stream
+        times = []
+        for i in range(a.warmup + a.iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _C.bulk_store_probe(dst.data_ptr(), total, rb, total, a.grid or sm * 2, stream)
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= a.warmup:
+                times.append(e0.elapsed_time(e1))
+        best = min(times)
+        print(json.dumps({"tag": a.tag or "bulk_store_probe", "row_bytes": rb, "peer": a.peer,
+                          "rows": total, "ms_best": best,
+                          "store_gbps_best": total * rb / best / 1e6,
+                          "grid": a.grid or sm * 2}))
+        return
     n, F = a.rows, a.cols
     rows_pad = (n + 255) // 256 * 256
     ssz = 8 if a.mode >= 3 else 4
