@@ -99,12 +99,18 @@ def parse_args():
     p.add_argument("--schema", choices=["f32", "dataspec"], default="f32",
                    help="f32: --cols float32 columns (BASELINE config 2/4); dataspec: the "
                         "reference's own DATA_SPEC table (key + 19 int64 + 1 float64, 168 B/row)")
-    p.add_argument("--row-align", type=int, default=0,
-                   help="pad the packed row pitch to a multiple of this (e.g. 128)")
+    p.add_argument("--row-align", type=int, default=None,
+                   help="pad the packed row pitch to a multiple of this (e.g. 128); 0 = never; "
+                        "default = the dataset's auto rule (96..127-byte rows -> 128)")
     p.add_argument("--min-timed-epochs", type=int, default=None,
                    help="time at least this many whole epochs (default: ours 20, reference 1)")
     p.add_argument("--max-concurrent-epochs", type=int, default=2,
                    help="epoch window (BASELINE config 3 compares 1 vs 2)")
+    p.add_argument("--reducers-per-trainer", type=int, default=1,
+                   help="reducer chunks per trainer (BASELINE config: 1). With more, the "
+                        "engine delivers an epoch in destination-chunk passes (K7) and "
+                        "`first_chunk_ms` reports when the first chunk became consumable")
+    p.add_argument("--chunk-passes", type=int, default=None)
     p.add_argument("--skip-e2e", action="store_true")
     p.add_argument("--time-budget-s", type=float, default=600.0,
                    help="reference arm: shrink the timed region (whole epochs, >= 1) so the "
@@ -302,6 +308,8 @@ def run_phase(ds, engine, torch, dist, world, warm_epochs, timed_epochs, d2h_eac
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
     kernel_ms = [engine.epoch_kernel_ms(e) for e in range(warm_epochs + window, n_ep + window)]
     kernel_ms = sorted(k for k in kernel_ms if k)
+    first_ms = sorted(m for m in (engine.first_pass_ms(e)
+                                  for e in range(warm_epochs + window, n_ep + window)) if m)
     # the same statistic on every rank: an epoch is only as fast as the slowest source
     med = torch.tensor([kernel_ms[len(kernel_ms) // 2] if kernel_ms else 0.0],
                        dtype=torch.float64, device=dev)
@@ -314,6 +322,7 @@ def run_phase(ds, engine, torch, dist, world, warm_epochs, timed_epochs, d2h_eac
             "launches": c1[0] - c0[0], "scatter_launches": c1[1] - c0[1],
             "h2d_bytes": c1[2] - c0[2], "epoch_sums": sums.cpu().tolist(),
             "kernel_ms": kernel_ms, "kernel_ms_per_rank": kernel_ms_per_rank,
+            "first_pass_ms": first_ms[len(first_ms) // 2] if first_ms else None,
             "checksum": checksum[0] if d2h_each_step else None}
 
 
@@ -358,13 +367,16 @@ def make_dataset(args, files, rank, world, epochs, resident, torch, seed=2026092
         opts["wait_mode"] = args.wait_mode
     if args.peer_alloc:
         opts["peer_alloc"] = args.peer_alloc
-    if args.row_align:
+    if args.row_align is not None:
         opts["row_align"] = args.row_align
     if resident == "host":
         opts["stream_chunk_rows"] = args.batch_size
+    if args.chunk_passes is not None:
+        opts["chunk_passes"] = args.chunk_passes
     fp8 = args.feature_dtype == "fp8"
     return TorchShufflingDataset(
-        files, epochs, world, args.batch_size, rank, num_reducers=world,
+        files, epochs, world, args.batch_size, rank,
+        num_reducers=world * args.reducers_per_trainer,
         max_concurrent_epochs=args.max_concurrent_epochs, feature_columns=feature_columns,
         feature_types=[dt] * len(feature_columns), label_column=label_column,
         label_type=dt if not fp8 else torch.float32, packed_features=True,
@@ -373,7 +385,8 @@ def make_dataset(args, files, rank, world, epochs, resident, torch, seed=2026092
 
 def shape_config(args, world):
     """The benchmark *shape*: identical keys and values in both arms."""
-    return {"model": f"TorchShufflingDataset {world} trainers x {world} reducers",
+    return {"model": f"TorchShufflingDataset {world} trainers x "
+                     f"{world * args.reducers_per_trainer} reducers",
             "global_batch": args.batch_size * world,
             "rows": args.rows_per_gpu * world, "cols": args.cols if args.schema == "f32" else 21,
             "schema": args.schema, "batch_size": args.batch_size, "seq_len": None,
@@ -426,7 +439,7 @@ def run_ours(args):
                    "backpressure": engine.backpressure, "peer_alloc": engine.peer_alloc,
                    "tmap_mode": engine.tmap_mode, "sched": engine.sched,
                    "row_bytes": row_pitch, "row_align": args.row_align,
-                   "fast_mode": fast_mode}
+                   "fast_mode": fast_mode, "chunk_passes": engine.chunk_passes}
     ds.dataset.close()
     steps = res["steps"]
     rows = timed_ep * args.rows_per_gpu * world       # rows delivered inside the region
@@ -484,6 +497,9 @@ def run_ours(args):
             "wall_ms_per_step": res["wall"] * 1e3 / steps,
             "ms_per_epoch": res["ms"] / timed_ep,
             "shuffle_kernel_ms_per_epoch": kernel_ms,
+            # K7: device time from the start of an epoch's shuffle until the first
+            # reducer chunk is consumable (== the whole epoch with a single pass)
+            "first_chunk_ms": res["first_pass_ms"] or kernel_ms,
             "shuffle_kernel_ms_min_max": [kms[0], kms[-1]] if kms else None,
             "shuffle_kernel_ms_per_rank": res["kernel_ms_per_rank"],
             "shuffle_kernel_gbps": (epoch_bytes / (kernel_ms / 1e3) / 1e9 if kernel_ms else None),

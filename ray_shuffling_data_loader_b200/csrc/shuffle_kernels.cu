@@ -104,6 +104,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+// RSDL_RACECHECK build (tools/sanitize.sh racecheck): compute-sanitizer's racecheck
+// models bar.sync / bar.arrive but not mbarrier arrive / try_wait issued from inline
+// PTX, so it reports the (mbarrier-ordered) index -> consumer hand-off of dptr[] as
+// a potential RAW hazard on every tile. In this build the hand-off is *also* fenced
+// with a named barrier per stage (ids 1..STAGES: the publishing index warp arrives,
+// the consumer warps sync), which the tool understands; the production build relies
+// on the mbarrier alone. The extra barrier cannot deadlock: it is reached in exactly
+// the same order as the mbarrier phases of the same stage.
+#ifdef RSDL_RACECHECK
+__device__ __forceinline__ void rc_arrive(int stage, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(stage + 1), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void rc_sync(int stage, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(stage + 1), "r"(nthreads) : "memory");
+}
+#else
+__device__ __forceinline__ void rc_arrive(int, int) {}
+__device__ __forceinline__ void rc_sync(int, int) {}
+#endif
+
 // cp.async.bulk global -> shared, completion reported on an mbarrier (SASS: UBLKCP).
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src,
                                             uint32_t bytes, uint64_t* bar) {
@@ -379,6 +399,7 @@ scatter_tma_kernel(const __grid_constant__ FastParams p) {
           for (int i = 0; i < kRows; ++i) sts64(&sm.dptr[stage][r + i * (32 * kIndexWarps)], prev[i]);
           __syncwarp();
           if (lane == 0) mbar_arrive(&sm.idx_full[stage]);
+          rc_arrive(stage, 32 * (kIndexWarps + kConsumerWarps));
           {
             const uint32_t col0 = panel * PANEL;
             const uint32_t ncols = min(static_cast<uint32_t>(PANEL), p.num_cols - col0);
@@ -462,6 +483,7 @@ scatter_tma_kernel(const __grid_constant__ FastParams p) {
         for (int i = 0; i < RPL; ++i) sts64(&sm.dptr[stage][lane + 32 * i], prev[i]);
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.idx_full[stage]);
+        rc_arrive(stage, 32 * (1 + kConsumerWarps));
         if (lane == 0 && panel + 1 == p.num_panels) mbar_arrive(&sm.turn[(w + 1) % kIndexWarps]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
@@ -489,6 +511,7 @@ scatter_tma_kernel(const __grid_constant__ FastParams p) {
       const uint32_t col0 = panel * PANEL;
       const uint32_t ncols = min(static_cast<uint32_t>(PANEL), p.num_cols - col0);
       mbar_wait(&sm.idx_full[stage], phase);
+      rc_sync(stage, 32 * ((coop ? kIndexWarps : 1) + kConsumerWarps));
       mbar_wait(&sm.full[stage], phase);
       const float* A = sm.tile[stage];
       for (int step = cwarp; step < kTileRows / 16; step += kConsumerWarps) {

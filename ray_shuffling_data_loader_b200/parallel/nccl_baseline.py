@@ -46,7 +46,10 @@ class _State:
         self.slots = torch.empty(n, dtype=torch.int64, device=dev)
         self.arange = torch.arange(n, dtype=torch.int64, device=dev)
         if world > 1:
-            mean = n / world
+            # block capacity must be IDENTICAL on every rank (equal-split collective):
+            # derive it from the largest source range, not from this rank's row count
+            n_max = -(-engine.plan.num_rows // world)
+            mean = n_max / world
             self.cap = int(math.ceil(mean + 12.0 * math.sqrt(mean) + 1024))
             blk = world * self.cap
             self.send_rows = torch.empty((blk, pitch), dtype=torch.uint8, device=dev)

@@ -196,12 +196,22 @@ class DeviceShuffleEngine:
         # only the rows whose slot falls in the k-th slice of every trainer's
         # buffer, each followed by its own produced flag. Cost: the source table is
         # re-read (and re-indexed) once per pass, which hides under the NVLink-bound
-        # stores when world > 1 (default there: up to 4 passes, never more than the
-        # reducer chunks per trainer) and is a real cost on one GPU (default 1).
-        # Host-streaming and the NCCL baseline always use one pass.
+        # stores when world > 1 (default there: as many passes as stay hidden, at most
+        # 4 and never more than the reducer chunks per trainer) and is a real cost on
+        # one GPU (default 1). Streaming modes and the NCCL baseline use one pass.
         max_chunks = max(self.plan.reducers_of_trainer(t) for t in range(self.plan.num_trainers))
         if chunk_passes is None:
-            chunk_passes = min(4, max_chunks) if world > 1 else 1
+            # A pass re-reads the source at the kernel's load-side rate (measured:
+            # ~3.0 TB/s, a pass of the 3.2 GB table costs 1.06 ms however few rows it
+            # delivers - profiles/README.md round 2), while the epoch as a whole is
+            # bound by NVLink egress (~0.68 TB/s achieved). Passes are free as long as
+            # a pass's share of the egress takes longer than its re-read.
+            chunk_passes = 1
+            if world > 1:
+                src_row = sum(L.itemsize(f.src_code) * f.width for f in self.layout.fields)
+                t_read = src_row / 3.0e12
+                t_link = self.layout.row_pitch * (world - 1) / world / 0.68e12
+                chunk_passes = max(1, min(4, max_chunks, int(t_link / max(t_read, 1e-30))))
         if resident != "hbm" or exchange == "nccl":
             chunk_passes = 1
         self.chunk_passes = max(1, min(int(chunk_passes), 64, max(1, self.plan.max_trainer_rows)))

@@ -550,3 +550,40 @@ def test_disk_streaming_matches_golden(tmp_path_factory, small_dataset, schema):
         dev.check_error()
     finally:
         dev.close(); cpu.close()
+
+
+def test_destination_offsets_beyond_4_gib():
+    """Byte offsets into an epoch buffer exceed 2^32 for the headline table already
+    (12.5 M x 256 B = 3.2 GB is close; 8-GPU wide rows are far beyond). A 5.1 GB
+    destination, 20 M rows x 64 f32, two trainers: sampled rows - specifically
+    including ones that land above the 4 GiB mark - carry the right bytes."""
+    C = _native()
+    free, _ = torch.cuda.mem_get_info()
+    if free < 14 * 2**30:
+        pytest.skip("needs ~11 GB of free device memory")
+    n, F, pitch = 20_000_000, 64, 256
+    rows_pad = (n + 255) // 256 * 256
+    src = torch.rand((F, rows_pad), dtype=torch.float32, device="cuda")
+    dst = torch.zeros((n, pitch), dtype=torch.uint8, device="cuda")       # one 5.12 GB block
+    assert dst.numel() > 2**32
+    T = 2
+    per = n // T
+    ptrs = torch.tensor([src[c].data_ptr() for c in range(F)], dtype=torch.int64, device="cuda")
+    key = perm.make_key(n, 77, 3)
+    stream = torch.cuda.current_stream().cuda_stream
+    C.scatter_fast(key=list(key.as_words()), num_rows=n, num_trainers=T, cols=ptrs.data_ptr(),
+                   num_cols=F, n_local=n, global_offset=0, row_pitch=pitch, scale_offset=0,
+                   dst=[dst.data_ptr(), dst.data_ptr() + per * pitch], mode=0,
+                   grid=C.sm_count(0), stream=stream, write_end=pitch)
+    torch.cuda.synchronize()
+    # sample source rows from all over the table; their positions are uniformly spread
+    idx = np.concatenate([np.arange(0, 50_000), np.arange(n - 50_000, n),
+                          np.random.default_rng(0).integers(0, n, 100_000)]).astype(np.uint64)
+    pos = perm.permute(idx, key).astype(np.int64)          # trainer t owns [t*per, (t+1)*per)
+    assert (pos * pitch > 2**32).sum() > 10_000            # the >4 GiB region is exercised
+    got = dst[torch.from_numpy(pos).cuda()].view(torch.float32)
+    want = src[:, torch.from_numpy(idx.astype(np.int64)).cuda()].t().contiguous()
+    assert torch.equal(got, want)
+    # every row written exactly once: the column-0 sums agree
+    assert torch.allclose(dst.view(torch.float32)[:, 0].sum(dtype=torch.float64),
+                          src[0, :n].sum(dtype=torch.float64), rtol=1e-9)
