@@ -111,6 +111,7 @@ def parse_args():
                         "engine delivers an epoch in destination-chunk passes (K7) and "
                         "`first_chunk_ms` reports when the first chunk became consumable")
     p.add_argument("--chunk-passes", type=int, default=None)
+    p.add_argument("--shuffle-priority", choices=["low", "high"], default=None)
     p.add_argument("--skip-e2e", action="store_true")
     p.add_argument("--time-budget-s", type=float, default=600.0,
                    help="reference arm: shrink the timed region (whole epochs, >= 1) so the "
@@ -287,6 +288,7 @@ def run_phase(ds, engine, torch, dist, world, warm_epochs, timed_epochs, d2h_eac
     ev0.record()
     for e in range(warm_epochs, n_ep):
         consume_epoch(e)
+    host_loop = time.perf_counter() - wall0       # host time to ENQUEUE the region's work
     # close the books: the next ``window`` epochs must be shuffled inside the region
     if not engine.wait_epochs_started(n_ep + window, 120.0):
         raise RuntimeError("shuffle driver did not start the trailing epochs")
@@ -319,6 +321,7 @@ def run_phase(ds, engine, torch, dist, world, warm_epochs, timed_epochs, d2h_eac
     kernel_ms_per_rank = [float(x.item()) for x in per_rank]
     return {"ms": float(ms.item()), "wall": float(wall_t.item()),
             "steps": steps_done[0] - warm_steps, "warm_steps": warm_steps,
+            "host_loop_s": host_loop,
             "launches": c1[0] - c0[0], "scatter_launches": c1[1] - c0[1],
             "h2d_bytes": c1[2] - c0[2], "epoch_sums": sums.cpu().tolist(),
             "kernel_ms": kernel_ms, "kernel_ms_per_rank": kernel_ms_per_rank,
@@ -373,6 +376,8 @@ def make_dataset(args, files, rank, world, epochs, resident, torch, seed=2026092
         opts["stream_chunk_rows"] = args.batch_size
     if args.chunk_passes is not None:
         opts["chunk_passes"] = args.chunk_passes
+    if args.shuffle_priority:
+        opts["shuffle_priority"] = args.shuffle_priority
     fp8 = args.feature_dtype == "fp8"
     return TorchShufflingDataset(
         files, epochs, world, args.batch_size, rank,
@@ -439,7 +444,8 @@ def run_ours(args):
                    "backpressure": engine.backpressure, "peer_alloc": engine.peer_alloc,
                    "tmap_mode": engine.tmap_mode, "sched": engine.sched,
                    "row_bytes": row_pitch, "row_align": args.row_align,
-                   "fast_mode": fast_mode, "chunk_passes": engine.chunk_passes}
+                   "fast_mode": fast_mode, "chunk_passes": engine.chunk_passes,
+                   "shuffle_priority": engine.shuffle_priority}
     ds.dataset.close()
     steps = res["steps"]
     rows = timed_ep * args.rows_per_gpu * world       # rows delivered inside the region
@@ -496,6 +502,9 @@ def run_ours(args):
             "scatter_launches_per_epoch": launches_per_epoch,
             "wall_ms_per_step": res["wall"] * 1e3 / steps,
             "ms_per_epoch": res["ms"] / timed_ep,
+            # host time spent enqueueing the region's steps (Python iterator + launches);
+            # well below ms_per_epoch = the device, not the host, sets the pace
+            "host_enqueue_ms_per_epoch": res["host_loop_s"] * 1e3 / timed_ep,
             "shuffle_kernel_ms_per_epoch": kernel_ms,
             # K7: device time from the start of an epoch's shuffle until the first
             # reducer chunk is consumable (== the whole epoch with a single pass)

@@ -303,6 +303,11 @@ scatter_tma_kernel(const __grid_constant__ FastParams p) {
     }
     for (int w = 0; w < kIndexWarps; ++w) mbar_init(&sm.turn[w], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // Pre-arm instead of waiting on "the phase before the first": every stage starts
+    // released (phase 0 of empty[s] completes here), so all waiters use the plain
+    // parity of their own iteration count.
+    for (int s = 0; s < STAGES; ++s)
+      for (int k = 0; k < kConsumerWarps; ++k) mbar_arrive(&sm.empty[s]);
   }
   __syncthreads();
 
@@ -317,7 +322,7 @@ scatter_tma_kernel(const __grid_constant__ FastParams p) {
       uint32_t phase = 0;
       for (unsigned long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
       for (uint32_t panel = 0; panel < p.num_panels; ++panel) {
-        mbar_wait(&sm.empty[stage], phase ^ 1);
+        mbar_wait(&sm.empty[stage], phase);
         mbar_arrive_expect_tx(&sm.full[stage], PANEL * kTileRows * 4u);   // SRC == 4 here
         if (dense) {
           // one [PANEL cols][TILE rows] box: 512-byte (or 1 KB) contiguous DRAM
@@ -348,7 +353,7 @@ scatter_tma_kernel(const __grid_constant__ FastParams p) {
       const uint32_t ncols = min(static_cast<uint32_t>(PANEL), p.num_cols - col0);
       const uint32_t per = (ncols + kLoaderWarps - 1) / kLoaderWarps;
       const uint32_t c_lo = min(warp * per, ncols), c_hi = min(c_lo + per, ncols);
-      mbar_wait(&sm.empty[stage], phase ^ 1);
+      mbar_wait(&sm.empty[stage], phase);
       if (lane == 0) mbar_arrive_expect_tx(&sm.full[stage], (c_hi - c_lo) * kTileRows * SRC);
       __syncwarp();
       for (uint32_t c = c_lo + lane; c < c_hi; c += 32) {
@@ -394,7 +399,7 @@ scatter_tma_kernel(const __grid_constant__ FastParams p) {
               ? dest_pointer(p.global_offset + lr, p.key, p.plan, p.dst, p.row_pitch) : 0ull;
         }
         for (uint32_t panel = 0; panel < p.num_panels; ++panel) {
-          mbar_wait(&sm.empty[stage], phase ^ 1);
+          mbar_wait(&sm.empty[stage], phase);
 #pragma unroll
           for (int i = 0; i < kRows; ++i) sts64(&sm.dptr[stage][r + i * (32 * kIndexWarps)], prev[i]);
           __syncwarp();
@@ -474,11 +479,14 @@ scatter_tma_kernel(const __grid_constant__ FastParams p) {
               : 0ull;
         }
       }
-      // the token: warp 0 holds it initially (waits for the phase *before* its round)
-      mbar_wait(&sm.turn[w], (round & 1u) ^ (w == 0 ? 1u : 0u));
+      // the token: warp 0 holds it initially, so its first round does not wait at all
+      // (round r of warp 0 waits for completion r-1 of turn[0], warp w > 0 for
+      // completion r of turn[w])
+      if (w != 0) mbar_wait(&sm.turn[w], round & 1u);
+      else if (round != 0) mbar_wait(&sm.turn[0], (round - 1u) & 1u);
       ++round;
       for (uint32_t panel = 0; panel < p.num_panels; ++panel) {
-        mbar_wait(&sm.empty[stage], phase ^ 1);
+        mbar_wait(&sm.empty[stage], phase);
 #pragma unroll
         for (int i = 0; i < RPL; ++i) sts64(&sm.dptr[stage][lane + 32 * i], prev[i]);
         __syncwarp();
@@ -981,13 +989,24 @@ __global__ void batch_sum_f32_kernel(const uint8_t* packed, unsigned long long r
 
 // Full-batch sink: fp64 sum of every fp32 word of a packed batch (reads the
 // whole batch once, 16 B per lane - the "trainer touched every byte" proof).
-__global__ void batch_sum_all_f32_kernel(const float4* data, unsigned long long nvec, double* out) {
+__global__ void __launch_bounds__(256) batch_sum_all_f32_kernel(const float4* data, unsigned long long nvec, double* out) {
+  // 4 independent 16-byte loads in flight per thread; the launcher keeps the grid at
+  // 4 CTAs per SM (1024 of the SM's 2048 threads) so that a co-running persistent
+  // kernel on another stream - the next epoch's scatter - can still be scheduled.
   double s = 0.0;
-  for (unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
-       i < nvec; i += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
-    float4 v = __ldg(data + i);
-    s += static_cast<double>(v.x) + static_cast<double>(v.y) + static_cast<double>(v.z) +
-         static_cast<double>(v.w);
+  const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+  unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+  for (; i + 3 * stride < nvec; i += 4 * stride) {
+    const float4 a = __ldg(data + i), b = __ldg(data + i + stride);
+    const float4 c = __ldg(data + i + 2 * stride), d = __ldg(data + i + 3 * stride);
+    s += (static_cast<double>(a.x) + static_cast<double>(a.y)) + (static_cast<double>(a.z) + static_cast<double>(a.w));
+    s += (static_cast<double>(b.x) + static_cast<double>(b.y)) + (static_cast<double>(b.z) + static_cast<double>(b.w));
+    s += (static_cast<double>(c.x) + static_cast<double>(c.y)) + (static_cast<double>(c.z) + static_cast<double>(c.w));
+    s += (static_cast<double>(d.x) + static_cast<double>(d.y)) + (static_cast<double>(d.z) + static_cast<double>(d.w));
+  }
+  for (; i < nvec; i += stride) {
+    const float4 v = __ldg(data + i);
+    s += (static_cast<double>(v.x) + static_cast<double>(v.y)) + (static_cast<double>(v.z) + static_cast<double>(v.w));
   }
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   __shared__ double part[8];
@@ -1226,7 +1245,7 @@ void launch_batch_sum_all_f32(const uint8_t* packed, unsigned long long nbytes, 
                               cudaStream_t stream) {
   const unsigned long long nvec = nbytes / 16;
   if (nvec == 0) return;
-  int grid = static_cast<int>(std::min<unsigned long long>((nvec + 255) / 256, 148 * 8));
+  int grid = static_cast<int>(std::min<unsigned long long>((nvec + 255) / 256, 148 * 4));
   batch_sum_all_f32_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(packed), nvec, out);
   check_launch("batch_sum_all_f32");
 }

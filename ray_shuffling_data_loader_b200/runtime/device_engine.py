@@ -113,7 +113,8 @@ class DeviceShuffleEngine:
                  use_tensor_map: bool = True, peer_alloc: Optional[str] = None,
                  backpressure: Optional[str] = None, numa_bind: Optional[bool] = None,
                  tmap_mode: Optional[int] = None, sched: Optional[int] = None,
-                 exchange_group=None, chunk_passes: Optional[int] = None):
+                 exchange_group=None, chunk_passes: Optional[int] = None,
+                 shuffle_priority: str = "low"):
         import torch
         self.C = load_native()
         self.torch = torch
@@ -146,15 +147,17 @@ class DeviceShuffleEngine:
         self.exchange_pg = exchange_group if exchange_group is not None else process_group
         self.stats = stats_collector
         self.window = max(1, int(max_concurrent_epochs))
-        # decode / staging threads: this rank's share of the CPUs it may run on
-        # (after NUMA binding), at most 32 - Parquet decode is the cold path's
-        # bottleneck and row groups decode independently
+        # decode / staging threads: this rank's share of the CPUs it may run on (after
+        # NUMA binding), at most 8. Measured on the 128-CPU box (tools/ingest_bench.py,
+        # 3.2 GB table in 25 row groups): 8 threads 1.32 s, 16 threads 1.5 - 1.6 s,
+        # 32 threads 2.2 - 2.5 s - Arrow's decode buffers and the per-thread pinned
+        # slots page-fault against each other beyond that.
         try:
             avail = len(os.sched_getaffinity(0))
         except AttributeError:
             avail = os.cpu_count() or 2
         share = avail // max(1, world) if not self.numa_cpus else avail // max(1, (world + 1) // 2)
-        self.num_threads = num_threads or max(2, min(32, share))
+        self.num_threads = num_threads or max(2, min(8, share))
         if resident not in ("hbm", "host", "disk"):
             raise ValueError("resident must be 'hbm', 'host' or 'disk'")
         if exchange not in ("p2p", "nccl"):
@@ -251,8 +254,18 @@ class DeviceShuffleEngine:
             self.chunk_rows = _align(self.chunk_rows, self.C.TILE_ROWS)
 
         prio_lo, prio_hi = self.C.stream_priority_range()
-        # The shuffle must not starve training kernels: lowest priority stream.
-        self.shuffle_stream = self.C.stream_create(prio_lo)
+        # The shuffle must not starve training kernels: lowest priority stream by
+        # default. Caveat (measured, profiles/README.md round 2): the scatter is a
+        # persistent kernel of one 512-thread CTA per SM; while a higher-priority
+        # stream keeps every SM's 2048 thread slots busy with back-to-back kernels,
+        # those CTAs wait for a slot and the epoch starts late. ``"high"`` lets the
+        # scatter claim its slots first (a trainer whose kernels need more than
+        # ~85 KB of shared memory per SM should keep "low").
+        if shuffle_priority not in ("low", "high"):
+            raise ValueError("shuffle_priority must be 'low' or 'high'")
+        self.shuffle_priority = shuffle_priority
+        self.shuffle_stream = self.C.stream_create(prio_lo if shuffle_priority == "low"
+                                                   else prio_hi)
         self.copy_stream = self.C.stream_create(prio_lo)
         self.poller = self.C.FlagPoller()
         self.host_pool = self.C.HostPool(self.num_threads)
@@ -561,14 +574,25 @@ class DeviceShuffleEngine:
                 for _ in range(nfiles):
                     self.stats.map_start(epoch)
             self._pinned: List[int] = []
+            if self.resident == "hbm":
+                reads = self._ingest_hbm_through_ring()
+                self._ingested = True
+                self.ingest_seconds = dur = timeit.default_timer() - t0
+                if self.stats is not None:
+                    for _ in range(nfiles):
+                        self.stats.map_done(epoch, dur / nfiles, float(np.mean(reads or [0.0])))
+                return
 
+            # resident="host": the whole decoded table stays pinned.
             # One pinned block, bump-allocated: same-shape columns end up with a
             # uniform stride, so a whole chunk moves with ONE cudaMemcpy2DAsync.
             dtypes = {f.name: np.dtype(L.numpy_storage_dtype(f.src_code)) for f in self.src_fields}
             widths = {f.name: f.width for f in self.src_fields}
             total = sum(_align(self.n_local * dtypes[n].itemsize * max(1, widths[n]))
                         for n in dict.fromkeys(f.name for f in self.src_fields)) + 4096
+            t_pin = timeit.default_timer()
             host_block, host_ptr = pinned_array(C, (total,), np.uint8)
+            self.pinned_alloc_seconds = timeit.default_timer() - t_pin
             self._pinned.append(host_ptr)
             cursor = {"off": 0}
             bump_lock = threading.Lock()
@@ -586,31 +610,11 @@ class DeviceShuffleEngine:
                 return host_block[off:off + nbytes].view(dt).reshape(shape)
 
             names = [f.name for f in self.src_fields]
-            # resident="hbm": every decoded column slice is handed to the copy engine
-            # the moment its row group is in pinned memory (decode || H2D), instead of
-            # copying whole columns after the last row group has been decoded.
-            by_name: Dict[str, List[int]] = {}
-            for i, f in enumerate(self.src_fields):
-                by_name.setdefault(f.name, []).append(i)
-            h2d_lock = threading.Lock()
-            dev_index = self.device_index
-
-            def stage(name, first_row, rows, colbuf):
-                C.set_device(dev_index)               # decode threads: device is per-thread
-                for i in by_name.get(name, ()):
-                    f = self.src_fields[i]
-                    isz = L.itemsize(f.src_code) * f.width
-                    with h2d_lock:
-                        C.memcpy_async(self.src_col_ptrs[0][i] + first_row * isz,
-                                       colbuf.ctypes.data + first_row * isz, rows * isz,
-                                       C.H2D, self.copy_stream)
-
             t_dec = timeit.default_timer()
             table = ingest.load_table(self.index, self.src_lo, self.src_lo + self.n_local,
                                       columns=list(dict.fromkeys(names)),
                                       num_threads=self.num_threads, alloc=alloc,
-                                      copy_fn=self._host_copy,
-                                      on_slice=stage if self.resident == "hbm" else None)
+                                      copy_fn=self._host_copy)
             self.decode_seconds = timeit.default_timer() - t_dec
             self.host_table = table
             self.host_cols = [table.columns[f.name] for f in self.src_fields]
@@ -618,14 +622,6 @@ class DeviceShuffleEngine:
                 want = np.dtype(L.numpy_storage_dtype(f.src_code))
                 if col.dtype != want:
                     raise TypeError(f"column {f.name}: decoded {col.dtype}, expected {want}")
-            if self.resident == "hbm":
-                C.stream_synchronize(self.copy_stream)     # the tail of the overlapped copies
-                # decoded host copy is no longer needed once resident in HBM
-                self.host_cols = None
-                self.host_table = None
-                for ptr in self._pinned:
-                    C.pinned_free(ptr)
-                self._pinned = []
             self._ingested = True
             dur = timeit.default_timer() - t0
             self.ingest_seconds = dur
@@ -633,6 +629,98 @@ class DeviceShuffleEngine:
             if self.stats is not None:
                 for _ in range(nfiles):
                     self.stats.map_done(epoch, dur / nfiles, float(np.mean(reads)))
+
+    def _ingest_hbm_through_ring(self) -> List[float]:
+        """Cold path for ``resident="hbm"``: Parquet -> HBM without ever pinning the
+        whole table. Every decode thread owns ONE pinned staging slot of row-group
+        size (allocated by the thread itself, so page-locking overlaps the other
+        threads' decoding - cudaHostAlloc costs ~0.27 s per GB and used to be 45 % of
+        the ingest); it decodes a row group straight into the slot (Arrow -> numpy
+        views over the slot), hands each column slice to the copy engine and only
+        waits for that copy when it needs the slot again. Decode, page-locking and
+        H2D all overlap; pinned memory in use = threads x one row group."""
+        from concurrent.futures import ThreadPoolExecutor
+        C = self.C
+        lo_all, hi_all = self.src_lo, self.src_lo + self.n_local
+        groups = [g for g in self.index.row_groups
+                  if g.global_start < hi_all and g.global_start + g.num_rows > lo_all and g.num_rows]
+        self.decode_seconds = 0.0
+        self.pinned_alloc_seconds = 0.0
+        if not groups:
+            return []
+        max_rows = max(min(hi_all, g.global_start + g.num_rows) - max(lo_all, g.global_start)
+                       for g in groups)
+        names = list(dict.fromkeys(f.name for f in self.src_fields))
+        first = {f.name: f for f in reversed(self.src_fields)}
+        host_off, off = {}, 0
+        for n in names:
+            f = first[n]
+            host_off[n] = off
+            off += _align(max_rows * L.itemsize(f.src_code) * max(1, f.width))
+        slot_bytes = max(off, 256)
+        by_name: Dict[str, List[int]] = {}
+        for i, f in enumerate(self.src_fields):
+            by_name.setdefault(f.name, []).append(i)
+        tls = threading.local()
+        slots, lock = [], threading.Lock()
+        stats_lock = threading.Lock()
+        reads: List[float] = []
+        t_alloc = [0.0]
+        dev_index = self.device_index
+
+        def work(g):
+            C.set_device(dev_index)                   # device is per-thread
+            slot = getattr(tls, "slot", None)
+            if slot is None:
+                t0 = timeit.default_timer()
+                arr, ptr = pinned_array(C, (slot_bytes,), np.uint8)
+                slot = tls.slot = {"arr": arr, "ptr": ptr, "copied": C.event_create(False),
+                                   "used": False}
+                with lock:
+                    slots.append(slot)
+                    t_alloc[0] += timeit.default_timer() - t0
+            elif slot["used"]:
+                C.event_synchronize(slot["copied"])   # previous row group has left the slot
+            lo, hi = max(lo_all, g.global_start), min(hi_all, g.global_start + g.num_rows)
+            bufs = {}
+            for n in names:
+                f = first[n]
+                dt = np.dtype(L.numpy_storage_dtype(f.src_code))
+                cnt = (hi - lo) * max(1, f.width)
+                view = slot["arr"][host_off[n]:host_off[n] + cnt * dt.itemsize].view(dt)
+                bufs[n] = view if f.width == 1 else view.reshape(hi - lo, f.width)
+            table = ingest.load_table(self.index, lo, hi, columns=names, num_threads=1,
+                                      prealloc=bufs)
+            for n in names:
+                if table.columns[n].dtype != bufs[n].dtype:
+                    raise TypeError(f"column {n}: decoded {table.columns[n].dtype}, "
+                                    f"expected {bufs[n].dtype}")
+            with lock:                                 # one enqueuer at a time per stream
+                for n in names:
+                    for i in by_name[n]:
+                        f = self.src_fields[i]
+                        isz = L.itemsize(f.src_code) * f.width
+                        C.memcpy_async(self.src_col_ptrs[0][i] + (lo - lo_all) * isz,
+                                       slot["ptr"] + host_off[n], (hi - lo) * isz, C.H2D,
+                                       self.copy_stream)
+                C.event_record(slot["copied"], self.copy_stream)
+            slot["used"] = True
+            with stats_lock:
+                reads.extend(table.read_durations or [])
+
+        t_dec = timeit.default_timer()
+        workers = max(1, min(self.num_threads, len(groups)))
+        with ThreadPoolExecutor(max_workers=workers, thread_name_prefix="ingest") as ex:
+            list(ex.map(work, groups))
+        C.stream_synchronize(self.copy_stream)
+        self.decode_seconds = timeit.default_timer() - t_dec
+        self.pinned_alloc_seconds = t_alloc[0] / max(1, len(slots))     # mean per thread
+        for slot in slots:
+            C.event_destroy(slot["copied"])
+            C.pinned_free(slot["ptr"])
+        self.host_cols = None
+        self.host_table = None
+        return reads
 
     # ------------------------------------------------------------------
     # one epoch

@@ -3,7 +3,7 @@ cd /root/repo
 mkdir -p gpurun_out
 TR8="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"
 TR4="python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1"
-run() { name=$1; shift; timeout 600 "$@" > gpurun_out/$name.json 2> gpurun_out/$name.err; echo "$name exit $?"; }
+run() { name=$1; shift; timeout 420 "$@" > gpurun_out/$name.json 2> gpurun_out/$name.err; echo "$name exit $?"; }
 run r2_bench_n8_ours $TR8 --master-port 29521 bench.py --gpus 8 --steps 20 --warmup 5 --keep-data
 run r2_bench_n8_ours_k7 $TR8 --master-port 29522 bench.py --gpus 8 --steps 20 --warmup 5 --keep-data --reducers-per-trainer 4 --skip-e2e
 run r2_bench_n8_nccl $TR8 --master-port 29523 bench.py --gpus 8 --steps 20 --warmup 5 --exchange nccl --skip-e2e
