@@ -31,7 +31,9 @@ import inspect
 import itertools
 import multiprocessing as mp
 import os
+import mmap
 import pickle
+import struct
 import shutil
 import sys
 import threading
@@ -106,11 +108,53 @@ def _path(oid):
     return os.path.join(_session(), "objects", oid)
 
 
+_MAGIC = b"RSHIM5\0\0"
+
+
 def _store(oid, value, is_error=False):
+    """Object file = header | pickle (protocol 5) | out-of-band buffers, 64-byte
+    aligned. Large numpy / pandas blocks travel out of band so that ``_load`` can map
+    them instead of copying them - what plasma gives real Ray (zero-copy reads of
+    immutable objects)."""
     tmp = _path(oid) + ".tmp" + uuid.uuid4().hex[:6]
+    bufs = []
+    try:
+        payload = pickle.dumps((is_error, value), protocol=5, buffer_callback=bufs.append)
+        raws = [b.raw() for b in bufs]
+    except (BufferError, ValueError, TypeError):
+        payload, raws = pickle.dumps((is_error, value), protocol=5), []   # in-band fallback
     with open(tmp, "wb") as f:
-        pickle.dump((is_error, value), f, protocol=5)
+        f.write(_MAGIC + struct.pack("<QQ", len(payload), len(raws))
+                + b"".join(struct.pack("<Q", r.nbytes) for r in raws))
+        f.write(payload)
+        pos = f.tell()
+        for r in raws:
+            pad = (-pos) % 64
+            f.write(b"\0" * pad)
+            f.write(r)
+            pos += pad + r.nbytes
     os.replace(tmp, _path(oid))
+
+
+def _read_object(path):
+    """-> (is_error, value); buffers are copy-on-write views of the mapped file."""
+    with open(path, "rb") as f:
+        size = os.fstat(f.fileno()).st_size
+        mm = mmap.mmap(f.fileno(), size, access=mmap.ACCESS_COPY) if size else None
+    view = memoryview(mm)
+    if bytes(view[:8]) != _MAGIC:
+        raise ValueError(f"{path}: not a ray_shim object")
+    plen, nbuf = struct.unpack_from("<QQ", view, 8)
+    sizes = struct.unpack_from(f"<{nbuf}Q", view, 24) if nbuf else ()
+    pos = 24 + 8 * nbuf
+    payload = view[pos:pos + plen]
+    pos += plen
+    buffers = []
+    for n in sizes:
+        pos += (-pos) % 64
+        buffers.append(view[pos:pos + n])
+        pos += n
+    return pickle.loads(payload, buffers=buffers)
 
 
 def _ready(oid):
@@ -121,8 +165,7 @@ _DELETE_ON_CONSUME = os.environ.get("RAY_SHIM_DELETE_ON_CONSUME", "1") == "1"
 
 
 def _load(oid, consume=False):
-    with open(_path(oid), "rb") as f:
-        is_error, value = pickle.load(f)
+    is_error, value = _read_object(_path(oid))      # (the mapping outlives the unlink below)
     if consume and _DELETE_ON_CONSUME:
         # No distributed ref-counting here: objects in this workload have exactly
         # one consumer (mapper partition -> its reducer, reducer output -> its
@@ -153,7 +196,7 @@ def get(refs, timeout=None, _consume=True):
             if deadline is not None and time.monotonic() > deadline:
                 raise exceptions.GetTimeoutError("Get timed out")
             time.sleep(sleep)
-            sleep = min(sleep * 1.5, 0.005)
+            sleep = min(sleep * 1.5, 0.001)
         out.append(_load(r.id, consume=_consume))
     return out[0] if single else out
 
@@ -169,7 +212,7 @@ def wait(refs, num_returns=1, timeout=None, fetch_local=True):
             rs = set(ready)
             return ready, [r for r in refs if r not in rs]
         time.sleep(sleep)
-        sleep = min(sleep * 1.5, 0.005)
+        sleep = min(sleep * 1.5, 0.001)
 
 
 # ---------------------------------------------------------------------------

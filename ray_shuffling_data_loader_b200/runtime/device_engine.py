@@ -204,15 +204,18 @@ class DeviceShuffleEngine:
         # one GPU (default 1). Streaming modes and the NCCL baseline use one pass.
         max_chunks = max(self.plan.reducers_of_trainer(t) for t in range(self.plan.num_trainers))
         if chunk_passes is None:
-            # A pass re-reads the source at the kernel's load-side rate (measured:
-            # ~3.0 TB/s, a pass of the 3.2 GB table costs 1.06 ms however few rows it
-            # delivers - profiles/README.md round 2), while the epoch as a whole is
-            # bound by NVLink egress (~0.68 TB/s achieved). Passes are free as long as
-            # a pass's share of the egress takes longer than its re-read.
+            # A pass re-reads the source at the kernel's load-side rate: ~3.0 TB/s alone
+            # (1.06 ms per pass of the 3.2 GB table however few rows it delivers), about
+            # 2.0 TB/s while its stores also fight for the link (N = 8, 3 passes: 1.53 ms
+            # per pass, epoch 4.62 instead of 4.14 ms - profiles/README.md round 2). The
+            # epoch as a whole is bound by NVLink egress (~0.68 TB/s). Passes are free
+            # only while a pass's share of the egress takes longer than its re-read, so
+            # the default is floor(t_link / t_read) with the pessimistic read rate:
+            # 2 passes at N >= 4, 1 at N = 2 for 256-byte f32 rows.
             chunk_passes = 1
             if world > 1:
                 src_row = sum(L.itemsize(f.src_code) * f.width for f in self.layout.fields)
-                t_read = src_row / 3.0e12
+                t_read = src_row / 2.0e12
                 t_link = self.layout.row_pitch * (world - 1) / world / 0.68e12
                 chunk_passes = max(1, min(4, max_chunks, int(t_link / max(t_read, 1e-30))))
         if resident != "hbm" or exchange == "nccl":
