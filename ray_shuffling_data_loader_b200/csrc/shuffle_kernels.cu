@@ -28,6 +28,8 @@
 #include <cuda_fp16.h>
 #include <cuda_fp8.h>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 
@@ -1245,8 +1247,19 @@ void launch_batch_sum_all_f32(const uint8_t* packed, unsigned long long nbytes, 
                               cudaStream_t stream) {
   const unsigned long long nvec = nbytes / 16;
   if (nvec == 0) return;
-  int grid = static_cast<int>(std::min<unsigned long long>((nvec + 255) / 256, 148 * 4));
-  batch_sum_all_f32_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(packed), nvec, out);
+  // CTAs per SM x threads per CTA of the bench sink (A/B knob: RSDL_SINK_GRID="ctas,threads")
+  static int ctas = 0, threads = 0;
+  if (ctas == 0) {
+    ctas = 4; threads = 256;
+    if (const char* e = std::getenv("RSDL_SINK_GRID")) {
+      int c = 0, t = 0;
+      if (std::sscanf(e, "%d,%d", &c, &t) == 2 && c > 0 && c <= 16 && t >= 32 && t <= 256 && t % 32 == 0) {
+        ctas = c; threads = t;
+      }
+    }
+  }
+  int grid = static_cast<int>(std::min<unsigned long long>((nvec + threads - 1) / threads, 148ull * ctas));
+  batch_sum_all_f32_kernel<<<grid, threads, 0, stream>>>(reinterpret_cast<const float4*>(packed), nvec, out);
   check_launch("batch_sum_all_f32");
 }
 

@@ -99,6 +99,19 @@ def pinned_array(C, shape, dtype) -> Tuple[np.ndarray, int]:
     return arr, ptr
 
 
+def default_chunk_passes(layout: L.RowLayout, world: int, max_chunks: int,
+                         read_bytes_per_s: float = 2.0e12, link_bytes_per_s: float = 0.68e12) -> int:
+    """How many destination-chunk passes stay hidden under the NVLink-bound stores:
+    ``floor(t_link / t_read)`` per source row (see DeviceShuffleEngine.__init__), at most 4
+    and at most the reducer chunks per trainer; 1 on a single GPU."""
+    if world <= 1:
+        return 1
+    src_row = sum(L.itemsize(f.src_code) * f.width for f in layout.fields)
+    t_read = src_row / read_bytes_per_s
+    t_link = layout.row_pitch * (world - 1) / world / link_bytes_per_s
+    return max(1, min(4, max_chunks, int(t_link / max(t_read, 1e-30))))
+
+
 class DeviceShuffleEngine:
     device = "cuda"
 
@@ -212,12 +225,7 @@ class DeviceShuffleEngine:
             # only while a pass's share of the egress takes longer than its re-read, so
             # the default is floor(t_link / t_read) with the pessimistic read rate:
             # 2 passes at N >= 4, 1 at N = 2 for 256-byte f32 rows.
-            chunk_passes = 1
-            if world > 1:
-                src_row = sum(L.itemsize(f.src_code) * f.width for f in self.layout.fields)
-                t_read = src_row / 2.0e12
-                t_link = self.layout.row_pitch * (world - 1) / world / 0.68e12
-                chunk_passes = max(1, min(4, max_chunks, int(t_link / max(t_read, 1e-30))))
+            chunk_passes = default_chunk_passes(self.layout, world, max_chunks)
         if resident != "hbm" or exchange == "nccl":
             chunk_passes = 1
         self.chunk_passes = max(1, min(int(chunk_passes), 64, max(1, self.plan.max_trainer_rows)))

@@ -185,6 +185,7 @@ class TorchShufflingDataset(IterableDataset):
             **dataset_options)
         self._transform: Optional[Callable] = None
         self._layout = None
+        self._slot_views = {}
 
     @property
     def dataset(self) -> ShufflingDataset:
@@ -209,9 +210,35 @@ class TorchShufflingDataset(IterableDataset):
             self._transform = layout
         return self._transform
 
+    def _buffer_views(self, buf):
+        """-> ``((features, label) views of the WHOLE epoch buffer, {(start, stop): batch})``.
+
+        On the GPU engine an epoch buffer is a slot of the device epoch ring: the same
+        memory every ``max_concurrent_epochs`` epochs, so both the whole-buffer views
+        and the per-batch slices are kept across epochs (keyed by device pointer and
+        row count) and a steady-state step costs two dictionary look-ups instead of
+        building tensor views - the Python side of a step matters once a step is only
+        tens of microseconds of device time (profiles/README.md, round 2)."""
+        whole = buf.view(0, buf.rows)
+        if isinstance(whole, np.ndarray):
+            whole = torch.from_numpy(whole)
+        self._layout = buf.layout
+        key = None
+        if whole.is_cuda:
+            key = (whole.data_ptr(), buf.rows, whole.shape[-1])
+            hit = self._slot_views.get(key)
+            if hit is not None:
+                return hit
+        entry = (packed_to_tensors(whole, buf.layout, self._spec, self._packed_features), {})
+        if key is not None:
+            if len(self._slot_views) >= 16:          # a ring never has that many slots
+                self._slot_views.clear()
+            self._slot_views[key] = entry
+        return entry
+
     def __iter__(self):
         from ray_shuffling_data_loader_b200.dataset import BatchSpan
-        cache = {}      # id(epoch buffer) -> (features, label) views of the WHOLE buffer
+        cache = {}      # id(epoch buffer) -> per-buffer entry (see _buffer_views)
         for item in iter(self._ds):
             if isinstance(item, BatchSpan) and hasattr(item.buffer.data, "_offset"):
                 # chunk shipped from the owning process (this rank only connected
@@ -220,26 +247,26 @@ class TorchShufflingDataset(IterableDataset):
                 item = item.packed()
             if isinstance(item, BatchSpan):
                 buf = item.buffer
-                views = cache.get(id(buf))
-                if views is None:
+                entry = cache.get(id(buf))
+                if entry is None:
                     if len(cache) > 8:
                         cache.clear()
-                    whole = buf.view(0, buf.rows)
-                    if isinstance(whole, np.ndarray):
-                        whole = torch.from_numpy(whole)
-                    self._layout = buf.layout
-                    views = cache[id(buf)] = (buf, packed_to_tensors(
-                        whole, buf.layout, self._spec, self._packed_features))
-                feats, label = views[1]
-                a, b = item.start, item.stop
-                # per batch: one row-slice per tensor of views built once per epoch
-                if isinstance(feats, list):
-                    f = [t[a:b] for t in feats]
-                elif isinstance(feats, tuple):
-                    f = tuple(t[a:b] for t in feats)
-                else:
-                    f = feats[a:b]
-                yield f, (label[a:b] if label is not None else None)
+                    entry = cache[id(buf)] = (buf, self._buffer_views(buf))
+                (feats, label), batches = entry[1]
+                key = (item.start, item.stop)
+                got = batches.get(key)
+                if got is None:
+                    a, b = key
+                    # one row-slice per tensor of views built once per buffer
+                    if isinstance(feats, list):
+                        f = [t[a:b] for t in feats]
+                    elif isinstance(feats, tuple):
+                        f = tuple(t[a:b] for t in feats)
+                    else:
+                        f = feats[a:b]
+                    got = batches[key] = (f, (label[a:b] if label is not None else None))
+                f, lab = got
+                yield (list(f) if isinstance(f, list) else f), lab
                 continue
             packed = item           # a batch that straddled two buffers (copy)
             if self._layout is None:

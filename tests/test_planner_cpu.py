@@ -208,3 +208,22 @@ def test_torch_layout_reorders_storage_not_tensors(small_dataset):
         assert features[1].dtype == torch.float32 and features[1].shape[1] == 1
         keys.append(features[0][:, 0].clone())
     assert sorted(torch.cat(keys).tolist()) == list(range(n))
+
+
+def test_default_chunk_passes_and_pass_of_row():
+    """K7 planning is pure Python: how many destination-chunk passes are free, and
+    which pass completes a given row range."""
+    from ray_shuffling_data_loader_b200.ops.plan import balanced_split
+    f32 = L.build_layout([(f"f{i}", L.DT_F32, L.DT_F32, 1) for i in range(64)])
+    assert DE.default_chunk_passes(f32, 1, 8) == 1            # one GPU: a pass is never free
+    assert DE.default_chunk_passes(f32, 2, 8) == 1            # 256 B rows, half of them remote
+    assert DE.default_chunk_passes(f32, 4, 8) == 2
+    assert DE.default_chunk_passes(f32, 8, 8) == 2
+    assert DE.default_chunk_passes(f32, 8, 1) == 1            # never more than the reducer chunks
+    bf16 = L.build_layout([(f"f{i}", L.DT_F32, L.DT_BF16, 1) for i in range(64)])
+    assert DE.default_chunk_passes(bf16, 8, 8) == 1           # half the bytes on the wire
+    eng = object.__new__(DE.DeviceShuffleEngine)
+    eng.chunk_passes = 3
+    eng.pass_bounds = balanced_split(10, 3)                   # [0,4) [4,7) [7,10)
+    assert [eng.pass_of_row(r) for r in (1, 4, 5, 7, 8, 10)] == [0, 0, 1, 1, 2, 2]
+    assert eng.pass_of_row(0) == 0
