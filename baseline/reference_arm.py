@@ -97,13 +97,15 @@ def main(args):
     t_construct = time.perf_counter()
     if rank == 0:
         ds = TorchShufflingDataset(files, epochs, world, args.batch_size, rank,
-                                   num_reducers=world * args.reducers_per_trainer, max_concurrent_epochs=window,
+                                   num_reducers=world * args.reducers_per_trainer,
+                                   max_concurrent_epochs=window,
                                    feature_columns=feature_columns, label_column=label_column)
     if world > 1:
         dist.barrier()
     if rank != 0:
         ds = TorchShufflingDataset(files, epochs, world, args.batch_size, rank,
-                                   num_reducers=world * args.reducers_per_trainer, max_concurrent_epochs=window,
+                                   num_reducers=world * args.reducers_per_trainer,
+                                   max_concurrent_epochs=window,
                                    feature_columns=feature_columns, label_column=label_column)
 
     sampler = bench.ClockSampler(range(world)) if rank == 0 else None

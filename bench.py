@@ -88,8 +88,9 @@ def parse_args():
     p.add_argument("--rows-per-gpu", type=int, default=ROWS_PER_GPU)
     p.add_argument("--cols", type=int, default=NUM_COLS)
     p.add_argument("--batch-size", type=int, default=BATCH_SIZE)
-    p.add_argument("--data-dir", default=os.environ.get("RSDL_BENCH_DIR",
-                                                         os.path.join(tempfile.gettempdir(), "rsdl_bench")))
+    p.add_argument("--data-dir",
+                   default=os.environ.get("RSDL_BENCH_DIR",
+                                          os.path.join(tempfile.gettempdir(), "rsdl_bench")))
     p.add_argument("--exchange", choices=["p2p", "nccl"], default="p2p")
     p.add_argument("--feature-dtype", choices=["float32", "bfloat16", "fp8"], default="float32")
     p.add_argument("--peer-alloc", choices=["symm", "ipc"], default=None)

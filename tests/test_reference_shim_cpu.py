@@ -57,3 +57,33 @@ def test_unmodified_reference_runs_on_the_shim(tmp_path):
                             timeout=250).returncode
     out = log.read_text()
     assert rc == 0 and "REFERENCE-OK" in out, out[-3000:]
+
+
+def test_shim_object_store_roundtrip_is_zero_copy(tmp_path, monkeypatch):
+    """The shim's object store writes numpy / pandas blocks out of band and maps them
+    back copy-on-write (plasma's zero-copy reads): values round-trip, arrays are
+    backed by the mapped file (not owned copies) and stay valid after the object is
+    consumed (unlinked)."""
+    import os
+    import sys
+    import numpy as np
+    import pandas as pd
+    shim = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "ray_shim")
+    monkeypatch.syspath_prepend(shim)
+    monkeypatch.setenv("RAY_SHIM_SESSION", f"pytest_store_{os.getpid()}")
+    for m in [m for m in sys.modules if m == "ray" or m.startswith("ray.")]:
+        monkeypatch.delitem(sys.modules, m)
+    import ray
+    ray.init(num_cpus=1)
+    try:
+        df = pd.DataFrame({"a": np.arange(100_000, dtype=np.int64), "b": np.random.rand(100_000)})
+        arr = np.arange(1 << 16, dtype=np.float32).reshape(256, 256)
+        ref = ray.put({"df": df, "arr": arr, "note": "x"})
+        out = ray.get(ref)
+        assert out["note"] == "x" and out["df"].equals(df) and np.array_equal(out["arr"], arr)
+        assert not out["arr"].flags.owndata            # a view of the mapped object file
+        out["arr"][0, 0] = -1.0                        # copy-on-write: private to this reader
+        assert out["arr"][0, 0] == -1.0
+        assert float(out["df"]["b"].sum()) == float(df["b"].sum())   # still readable after unlink
+    finally:
+        ray.shutdown()
