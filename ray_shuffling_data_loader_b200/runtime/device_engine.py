@@ -4,22 +4,30 @@ One instance per process (= per GPU). It replaces, for the GPU path, everything
 the reference runs as Ray tasks per epoch (``shuffle_map``/``shuffle_reduce``,
 reference ``shuffle.py:129-200``) and everything Ray's object store does for it:
 
-* **ingest** - the rows this rank owns are decoded once (``runtime/ingest.py``)
-  into *pinned* host buffers and staged into HBM with ``cudaMemcpyAsync`` on a
-  copy stream (kernel-table rows K9/K10). ``resident="hbm"`` keeps the columnar
-  table on the device for every epoch; ``resident="host"`` keeps it in pinned
-  memory and re-streams it chunk by chunk each epoch (double-buffered H2D that
-  overlaps the scatter kernel) for datasets that do not fit.
-* **epoch ring** (K11) - ``max_concurrent_epochs`` destination slots per local
-  trainer inside one ``cudaMalloc`` arena that is exported with CUDA IPC and
-  mapped by every peer, plus epoch-tagged signal words in the same arena:
-  ``produced[slot][src_rank]`` (written by each source after its scatter kernel)
-  and ``consumed[trainer]`` (written on the trainer's stream when it has finished
-  an epoch - the device analogue of ``task_done`` + ``queue.join()``).
-* **exchange** - one fused kernel launch per (epoch, source chunk) pushes every
-  row to its final ``(trainer, slot)`` in local or peer HBM
-  (``csrc/shuffle_kernels.cu``); ``exchange="nccl"`` swaps in the NCCL
-  ``all_to_all_single`` baseline (``parallel/nccl_baseline.py``).
+* **ingest** - the rows this rank owns are decoded once (``runtime/ingest.py``),
+  row group by row group, each decode thread staging through its own pinned slot
+  into the HBM-resident columnar table with ``cudaMemcpyAsync`` on a copy stream
+  (kernel-table rows K9/K10; decode, page-locking and H2D overlap).
+  ``resident="hbm"`` keeps the table on the device for every epoch;
+  ``resident="host"`` keeps it in pinned memory and re-streams it chunk by chunk
+  each epoch (double-buffered H2D that overlaps the scatter kernel);
+  ``resident="disk"`` keeps nothing and re-decodes the row groups every epoch
+  through a bounded pinned ring (tables larger than host memory - the reference's
+  only mode, ``shuffle.py:151``).
+* **epoch ring** (K7, K11) - ``max_concurrent_epochs`` destination slots per local
+  trainer inside one arena that every peer maps (VMM symmetric allocation, or
+  ``cudaMalloc`` + CUDA IPC), plus epoch-tagged signal words in the same arena:
+  ``produced[slot][pass][src_rank]`` (written by each source after each
+  destination-chunk pass of its scatter) and ``consumed[trainer]`` (written on the
+  trainer's stream when it has finished an epoch - the device analogue of
+  ``task_done`` + ``queue.join()``).
+* **exchange** - one fused kernel launch per (epoch, destination-chunk pass[,
+  source chunk]) pushes every row to its final ``(trainer, slot)`` in local or peer
+  HBM (``csrc/shuffle_kernels.cu``); a reducer chunk is consumable as soon as the
+  pass that delivers it has completed on every source (reference
+  ``dataset.py:133-139``: start on the first finished reducer output).
+  ``exchange="nccl"`` swaps in the NCCL ``all_to_all_single`` baseline
+  (``parallel/nccl_baseline.py``).
 
 Every wait on a flag has a timeout and raises a clear error instead of hanging
 (the reference deadlocks on a dead trainer).
@@ -921,8 +929,8 @@ class DeviceShuffleEngine:
     def _stream_epoch_disk(self, key_words, dst, epoch: int):
         """resident='disk' - tables larger than pinned host memory (the reference's
         only mode: it re-reads Parquet every epoch, ``shuffle.py:151``). Row groups
-        are decoded by a bounded pool into a ring of pinned staging buffers
-        (``disk_prefetch`` + 2 of them, each one row group), copied to one of two
+        are decoded by a bounded pool into a ring of pinned staging buffers (decode
+        threads + 2 of them, each one row group), copied to one of two
         device staging buffers and scattered; decode of the next row groups, the
         H2D of this one and the scatter of the previous one overlap. Host memory
         in use is bounded by the ring, not by the table."""
