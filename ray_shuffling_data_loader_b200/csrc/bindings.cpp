@@ -771,6 +771,44 @@ PYBIND11_MODULE(_C, m) {
         py::arg("pool"), py::arg("key"), py::arg("num_rows"), py::arg("num_trainers"),
         py::arg("packed"), py::arg("row_pitch"), py::arg("global_offset"), py::arg("n_local"),
         py::arg("dst"));
+  // K7 on the host backend: deliver destination positions [pos_lo, pos_hi) in order by
+  // *pulling* each one's source row through the inverse permutation. Same bytes as the
+  // scatter above, but a destination chunk is complete the moment its range is done, so
+  // the CPU engine can hand out reducer chunks one by one.
+  m.def("host_gather_rows",
+        [](HostPool& pool, const std::vector<uint64_t>& key, uintptr_t packed, uint32_t row_pitch,
+           uint64_t global_offset, uint64_t n_local, uint64_t pos_lo, uint64_t pos_hi,
+           uintptr_t dst) {
+          const PermKeyDev k = make_key(key);
+          const uint8_t* src = as_ptr<const uint8_t>(packed);
+          uint8_t* out = as_ptr<uint8_t>(dst);
+          py::gil_scoped_release r;
+          pool.parallel_for(pos_hi - pos_lo, 1 << 14, [&](size_t b, size_t e) {
+            // random row *reads* are latency bound: resolve a block of source rows and
+            // prefetch their first lines before copying any of them
+            constexpr size_t kBlock = 32;
+            unsigned long long gi[kBlock];
+            for (size_t i0 = b; i0 < e; i0 += kBlock) {
+              const size_t m = std::min(kBlock, e - i0);
+              for (size_t j = 0; j < m; ++j) {
+                gi[j] = rsdl_permute_inv(pos_lo + i0 + j, k);
+                if (gi[j] >= global_offset && gi[j] < global_offset + n_local) {
+                  const uint8_t* row = src + (gi[j] - global_offset) * row_pitch;
+                  for (uint32_t o = 0; o < row_pitch; o += 64) __builtin_prefetch(row + o, 0, 0);
+                }
+              }
+              for (size_t j = 0; j < m; ++j) {
+                if (gi[j] < global_offset || gi[j] >= global_offset + n_local)
+                  continue;                           // row owned by another process
+                std::memcpy(out + (i0 + j) * row_pitch,
+                            src + (gi[j] - global_offset) * row_pitch, row_pitch);
+              }
+            }
+          });
+        },
+        py::arg("pool"), py::arg("key"), py::arg("packed"), py::arg("row_pitch"),
+        py::arg("global_offset"), py::arg("n_local"), py::arg("pos_lo"), py::arg("pos_hi"),
+        py::arg("dst"));
   py::class_<FlagPoller>(m, "FlagPoller")
       .def(py::init<>())
       .def("wait",

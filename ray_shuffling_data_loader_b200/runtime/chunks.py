@@ -38,6 +38,8 @@ class EpochBuffer:
         self._wait_fn = wait_fn
         self._release_fn = release_fn
         self._ready = threading.Event()
+        self._rows_cv = threading.Condition()
+        self._rows_ready = 0          # rows [0, _rows_ready) have landed (CPU engine, K7)
         self._error: Optional[BaseException] = None
         self._released = False
         if wait_fn is None and device != "cpu":
@@ -46,7 +48,18 @@ class EpochBuffer:
     # producer side (CPU engine) -----------------------------------------
     def mark_ready(self, error: Optional[BaseException] = None):
         self._error = error
-        self._ready.set()
+        with self._rows_cv:
+            if error is None:
+                self._rows_ready = self.rows
+            self._ready.set()
+            self._rows_cv.notify_all()
+
+    def mark_rows_ready(self, row_stop: int):
+        """Rows ``[0, row_stop)`` are final (the host engine fills a buffer chunk by
+        chunk, in order): wakes consumers that wait for a prefix only."""
+        with self._rows_cv:
+            self._rows_ready = max(self._rows_ready, int(row_stop))
+            self._rows_cv.notify_all()
 
     # consumer side ---------------------------------------------------------
     def wait(self, timeout: Optional[float] = None, row_stop: Optional[int] = None):
@@ -58,7 +71,11 @@ class EpochBuffer:
             else:
                 self._wait_fn(timeout, row_stop)
             return
-        if not self._ready.wait(timeout):
+        need = self.rows if row_stop is None else min(int(row_stop), self.rows)
+        with self._rows_cv:
+            ok = self._rows_cv.wait_for(
+                lambda: self._rows_ready >= need or self._ready.is_set(), timeout)
+        if not ok:
             raise TimeoutError(
                 f"epoch {self.epoch} buffer of trainer {self.trainer} not ready "
                 f"after {timeout}s")

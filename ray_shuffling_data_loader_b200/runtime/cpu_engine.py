@@ -188,32 +188,29 @@ class CpuShuffleEngine:
                     self.stats.reduce_start(epoch)
             key = perm.make_key(self.plan.num_rows, self.seed, epoch)
             n_local = self._packed.shape[0]
-            if self.C is not None and n_local:
-                # native path: pi_e + scatter on the C++ worker pool, GIL released
+            if self.world == 1:
+                # K7 on the host: every row is local, so the epoch is produced in
+                # destination order - reducer chunk by reducer chunk, round-robin over
+                # the trainers - by pulling each position's source row through the
+                # inverse permutation (same bytes as a scatter, sequential writes).
+                # A chunk is handed out the moment its range is complete (reference
+                # dataset.py:133-139: start on the first finished reducer output).
+                self._gather_in_chunk_order(key, buffers)
+            elif self.C is not None and n_local:
+                # native path: pi_e on the C++ worker pool, GIL released
                 words = list(key.as_words())
                 T = self.plan.num_trainers
-                if self.world == 1:
-                    dst = [buffers[t].data.ctypes.data if t in buffers else 0 for t in range(T)]
-                    self.C.host_scatter_rows(self._host_pool, words, self.plan.num_rows, T,
-                                             self._packed.ctypes.data, self.layout.row_pitch,
-                                             self._offset, n_local, dst)
-                else:
-                    trainer = np.empty(n_local, dtype=np.int32)
-                    slot = np.empty(n_local, dtype=np.int64)
-                    self.C.host_perm_positions(self._host_pool, words, self.plan.num_rows, T,
-                                               self._offset, n_local, trainer.ctypes.data,
-                                               slot.ctypes.data)
-                    self._exchange(trainer, slot, buffers[self.rank])
+                trainer = np.empty(n_local, dtype=np.int32)
+                slot = np.empty(n_local, dtype=np.int64)
+                self.C.host_perm_positions(self._host_pool, words, self.plan.num_rows, T,
+                                           self._offset, n_local, trainer.ctypes.data,
+                                           slot.ctypes.data)
+                self._exchange(trainer, slot, buffers[self.rank])
             else:
                 gidx = np.arange(self._offset, self._offset + n_local, dtype=np.uint64)
                 pos = perm.permute(gidx, key)
                 trainer, slot = self.plan.position_to_trainer(pos)
-                if self.world == 1:
-                    for t, buf in buffers.items():
-                        sel = np.nonzero(trainer == t)[0]
-                        buf.data[slot[sel]] = self._packed[sel]
-                else:
-                    self._exchange(trainer, slot, buffers[self.rank])
+                self._exchange(trainer, slot, buffers[self.rank])
             dur = timeit.default_timer() - t0
             if self.stats is not None:
                 for _ in range(self.plan.num_reducers):
@@ -223,6 +220,28 @@ class CpuShuffleEngine:
         except BaseException as e:  # surface in the consumer, not the pool
             for buf in buffers.values():
                 buf.mark_ready(e)
+
+    def _gather_in_chunk_order(self, key, buffers: Dict[int, EpochBuffer]):
+        plan, pitch = self.plan, self.layout.row_pitch
+        n_local = self._packed.shape[0]
+        words = list(key.as_words())
+        chunks = {t: plan.trainer_chunks(t) for t in buffers}
+        for c in range(max((len(v) for v in chunks.values()), default=0)):
+            for t, buf in buffers.items():
+                if c >= len(chunks[t]):
+                    continue
+                a, b = chunks[t][c]
+                start = plan.trainer_range(t)[0]
+                if b > a and n_local:
+                    if self.C is not None:
+                        self.C.host_gather_rows(self._host_pool, words, self._packed.ctypes.data,
+                                                pitch, self._offset, n_local, start + a, start + b,
+                                                buf.data.ctypes.data + a * pitch)
+                    else:
+                        pos = np.arange(start + a, start + b, dtype=np.uint64)
+                        src = perm.inverse(pos, key).astype(np.int64) - self._offset
+                        buf.data[a:b] = self._packed[src]
+                buf.mark_rows_ready(b)
 
     def _exchange(self, trainer: np.ndarray, slot: np.ndarray, buf: EpochBuffer):
         """Row exchange over gloo: the host analogue of the NVLink scatter."""

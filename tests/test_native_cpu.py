@@ -156,3 +156,44 @@ def test_cpu_engine_recycles_released_buffers(small_dataset):
     tds.set_epoch(0)
     for _ in tds:
         pass
+
+
+@pytest.mark.parametrize("native", [True, False])
+def test_cpu_engine_delivers_chunks_in_order_and_matches_forward_scatter(small_dataset, native):
+    """K7 on the host backend: the epoch is produced reducer chunk by reducer chunk through
+    the inverse permutation. (a) waiting for a chunk's rows only returns a complete prefix,
+    (b) the result equals an independent forward scatter pi_e(i) -> (trainer, slot)."""
+    from ray_shuffling_data_loader_b200.ops import layout as L
+    from ray_shuffling_data_loader_b200.ops import perm
+    from ray_shuffling_data_loader_b200.runtime import ingest
+    from ray_shuffling_data_loader_b200.runtime.cpu_engine import CpuShuffleEngine
+    files, n = small_dataset
+    plan_args = dict(num_trainers=3, num_reducers=11, batch_size=500, drop_last=False)
+    eng = CpuShuffleEngine(files, plan_args, L.dataframe_layout, 21, native=native)
+    try:
+        # independent golden: decode, pack, forward scatter with the public permutation
+        idx = ingest.scan_files(files)
+        lay = L.dataframe_layout(idx.schema)
+        table = ingest.load_table(idx, 0, n, columns=lay.names)
+        packed = L.pack_rows(table.columns, lay)
+        for epoch in (0, 1):
+            key = perm.make_key(n, 21, epoch)
+            pos = perm.permute(np.arange(n, dtype=np.uint64), key)
+            trainer, slot = eng.plan.position_to_trainer(pos)
+            bufs = eng.start_epoch(epoch)
+            seen = {t: [] for t in bufs}
+            for t, buf in bufs.items():
+                want = np.zeros_like(buf.data)
+                sel = trainer == t
+                want[slot[sel]] = packed[sel]
+                for a, b in eng.plan.trainer_chunks(t):
+                    buf.wait(60, row_stop=b)                  # this chunk (and all before it)
+                    assert buf._rows_ready >= b
+                    seen[t].append(buf._rows_ready)
+                    assert np.array_equal(buf.data[:b], want[:b]), (epoch, t, a, b)
+                buf.wait(60)
+                assert np.array_equal(buf.data, want)
+                buf.release()
+            assert all(v == sorted(v) for v in seen.values())
+    finally:
+        eng.close()
