@@ -730,6 +730,37 @@ PYBIND11_MODULE(_C, m) {
         },
         py::arg("pool"), py::arg("fields"), py::arg("num_fields"), py::arg("num_rows"),
         py::arg("row_pitch"), py::arg("out"));
+  // packed rows -> one contiguous array per field (the inverse of host_pack_rows without
+  // casts: fields keep their packed dtype). `fields`: host array of FieldDev whose `src`
+  // is the DESTINATION column base and whose `width * itemsize(dst_code)` bytes at
+  // `dst_off` of every row are copied. Used to turn a reducer chunk into DataFrame
+  // columns once, on all cores, instead of slicing rows batch by batch in Python.
+  m.def("host_unpack_fields",
+        [](HostPool& pool, uintptr_t packed, uint64_t num_rows, uint32_t row_pitch,
+           uintptr_t fields, uint32_t num_fields) {
+          const FieldDev* f = as_ptr<const FieldDev>(fields);
+          const uint8_t* in = as_ptr<const uint8_t>(packed);
+          py::gil_scoped_release r;
+          pool.parallel_for(num_rows, 8192, [&](size_t b, size_t e) {
+            for (uint32_t i = 0; i < num_fields; ++i) {
+              const size_t nb = static_cast<size_t>(f[i].width) * rsdl_itemsize(f[i].dst_code);
+              uint8_t* out = const_cast<uint8_t*>(f[i].src);
+              const uint8_t* src = in + f[i].dst_off;
+              if (nb == 8) {
+                for (size_t r2 = b; r2 < e; ++r2)
+                  std::memcpy(out + r2 * 8, src + r2 * row_pitch, 8);
+              } else if (nb == 4) {
+                for (size_t r2 = b; r2 < e; ++r2)
+                  std::memcpy(out + r2 * 4, src + r2 * row_pitch, 4);
+              } else {
+                for (size_t r2 = b; r2 < e; ++r2)
+                  std::memcpy(out + r2 * nb, src + r2 * row_pitch, nb);
+              }
+            }
+          });
+        },
+        py::arg("pool"), py::arg("packed"), py::arg("num_rows"), py::arg("row_pitch"),
+        py::arg("fields"), py::arg("num_fields"));
   m.def("host_perm_positions",
         [](HostPool& pool, const std::vector<uint64_t>& key, uint64_t num_rows,
            uint32_t num_trainers, uint64_t global_offset, uint64_t n_local, uintptr_t trainer,

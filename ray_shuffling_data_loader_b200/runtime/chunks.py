@@ -169,21 +169,63 @@ def _to_numpy(packed) -> np.ndarray:
 # packed rows -> user-facing objects
 # ---------------------------------------------------------------------------
 
+_FIELD_DESC = np.dtype([("ptr", "<u8"), ("src_code", "<u4"), ("dst_code", "<u4"),
+                        ("dst_off", "<u4"), ("width", "<u4")])
+_NATIVE = {"C": None, "pool": None, "tried": False}
+
+
+def _native_unpacker():
+    """(extension module, shared worker pool) for ``host_unpack_fields``, or (None, None)
+    when the extension is not built / disabled (``RSDL_CPU_NATIVE=0``)."""
+    if not _NATIVE["tried"]:
+        _NATIVE["tried"] = True
+        import os
+        if os.environ.get("RSDL_CPU_NATIVE", "1") != "0":
+            try:
+                from ray_shuffling_data_loader_b200 import _C
+                _NATIVE["C"] = _C
+                _NATIVE["pool"] = _C.HostPool(max(1, min(16, (os.cpu_count() or 2))))
+            except Exception:
+                _NATIVE["C"] = None
+    return _NATIVE["C"], _NATIVE["pool"]
+
+
+def unpack_columns(packed: np.ndarray, layout: L.RowLayout) -> Dict[str, np.ndarray]:
+    """Packed rows -> one owned, contiguous array per display field (``[n]`` or
+    ``[n, width]`` in the field's storage dtype). With the extension built this is one
+    multi-threaded transposition pass (``host_unpack_fields``); otherwise numpy copies."""
+    fields = list(layout.display_fields)
+    n = int(packed.shape[0])
+    C, pool = _native_unpacker()
+    if C is None or n < 4096 or not packed.flags.c_contiguous:
+        return {f.name: L.unpack_field(packed, f) for f in fields}
+    out, desc = {}, np.zeros(len(fields), dtype=_FIELD_DESC)
+    for i, f in enumerate(fields):
+        dt = L.numpy_storage_dtype(f.dst_code)
+        arr = np.empty((n,) if f.width == 1 else (n, f.width), dtype=dt)
+        out[f.name] = arr
+        desc[i] = (arr.ctypes.data, f.src_code, f.dst_code, f.offset, f.width)
+    C.host_unpack_fields(pool, packed.ctypes.data, n, int(packed.shape[1]), desc.ctypes.data,
+                         len(fields))
+    return out
+
+
 def packed_to_dataframe(packed: np.ndarray, layout: L.RowLayout):
     """Rebuild a pandas DataFrame (what the reference's iterator yields,
     ``dataset.py:108-188``) from packed rows. List-valued fields become object
-    columns of ndarrays, like Parquet list columns read by pandas."""
+    columns of ndarrays, like Parquet list columns read by pandas. The columns are
+    owned copies (the packed buffer may be recycled) handed to pandas without a
+    second, consolidating copy."""
     import pandas as pd
-    cols = {}
+    cols = unpack_columns(packed, layout)
     for f in layout.display_fields:
-        vals = L.unpack_field(packed, f)
         if f.width > 1:
+            vals = cols[f.name]
             obj = np.empty(len(vals), dtype=object)
             for i in range(len(vals)):
                 obj[i] = vals[i]
-            vals = obj
-        cols[f.name] = vals
-    return pd.DataFrame(cols)
+            cols[f.name] = obj
+    return pd.DataFrame(cols, copy=False)
 
 
 def field_tensor(packed, f: L.Field, pitch: int):
