@@ -20,6 +20,7 @@
 #include <string>
 #include <thread>
 #include <type_traits>
+#include <tuple>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -554,8 +555,29 @@ PYBIND11_MODULE(_C, m) {
            uint32_t row_pitch, uint32_t scale_offset, const std::vector<uintptr_t>& dst, int mode,
            int grid, uintptr_t stream, uintptr_t col_base, uint64_t col_stride,
            uint64_t rows_alloc, int tmap_mode, uintptr_t kinds, uint32_t write_end, int sched,
-           uint64_t slot_lo, uint64_t slot_hi) {
+           uint64_t slot_lo, uint64_t slot_hi,
+           const std::vector<std::tuple<uintptr_t, uint32_t, uint32_t, uint32_t>>& tail,
+           uint32_t tail_lo, uint32_t tail_hi) {
           FastParams p;
+          if (tail.size() > RSDL_MAX_TAIL_FIELDS)
+            throw std::runtime_error("scatter_fast: too many tail fields");
+          if (tail_hi > tail_lo && ((tail_lo | tail_hi) & 15u || tail_hi > row_pitch))
+            throw std::runtime_error("scatter_fast: tail range must be 16-byte multiples inside the row");
+          p.tail_lo = tail_lo;
+          p.tail_hi = tail_hi > tail_lo ? tail_hi : tail_lo;
+          p.num_tail = static_cast<uint32_t>(tail.size());
+          p.pad_ = 0;
+          for (size_t i = 0; i < RSDL_MAX_TAIL_FIELDS; ++i) {
+            p.tail[i] = rsdl::TailField{nullptr, 0, 0, 0, 0};
+            if (i < tail.size()) {
+              const uint32_t dsz = rsdl_itemsize(std::get<2>(tail[i]));
+              const uint32_t doff = std::get<3>(tail[i]);
+              if ((dsz != 4 && dsz != 8) || doff % dsz || doff < tail_lo || doff + dsz > tail_hi)
+                throw std::runtime_error("scatter_fast: bad tail field");
+              p.tail[i] = rsdl::TailField{as_ptr<const uint8_t>(std::get<0>(tail[i])),
+                                          std::get<1>(tail[i]), std::get<2>(tail[i]), doff, 0};
+            }
+          }
           std::memset(&p.tmap, 0, sizeof(p.tmap));
           p.use_tmap = 0;
           const uint32_t tile_rows = static_cast<uint32_t>(rsdl::fast_tile_rows(mode));
@@ -595,7 +617,9 @@ PYBIND11_MODULE(_C, m) {
         py::arg("stream"), py::arg("col_base") = 0, py::arg("col_stride") = 0,
         py::arg("rows_alloc") = 0, py::arg("tmap_mode") = 2, py::arg("kinds") = 0,
         py::arg("write_end") = 0, py::arg("sched") = -1, py::arg("slot_lo") = 0,
-        py::arg("slot_hi") = ~0ull);
+        py::arg("slot_hi") = ~0ull,
+        py::arg("tail") = std::vector<std::tuple<uintptr_t, uint32_t, uint32_t, uint32_t>>{},
+        py::arg("tail_lo") = 0, py::arg("tail_hi") = 0);
   m.def("fast_src_itemsize", &rsdl::fast_src_itemsize);
   m.def("fast_ctas_per_sm", &rsdl::fast_ctas_per_sm);
   m.def("scatter_generic",

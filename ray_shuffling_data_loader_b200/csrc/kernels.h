@@ -12,6 +12,20 @@ namespace rsdl {
 
 // Fast path: every source column is a 4-byte (modes 0-2) or 8-byte (modes 3-4)
 // scalar (see shuffle_kernels.cu).
+// A small scalar field that follows the fast prefix in the packed row (a float32 label
+// behind fp8 / bf16 / int64 features, an int64 id behind float features ...). The fast
+// kernel loads it straight from its source column and folds it into the 16-byte group
+// store of its row, so a mixed row costs no second kernel and no extra sub-sector
+// write transaction per row (profiles/README.md round 2, "bytes on the wire").
+struct TailField {
+  const uint8_t* src;                // source column (chunk-local, like FastParams::cols)
+  uint32_t src_code;
+  uint32_t dst_code;                 // 4- or 8-byte destination types only
+  uint32_t dst_off;                  // byte offset in the row, aligned to the dst itemsize
+  uint32_t pad_;
+};
+#define RSDL_MAX_TAIL_FIELDS 4
+
 struct FastParams {
   alignas(64) CUtensorMap tmap;      // [num_cols][rows] view of the source columns
   uint32_t use_tmap;                 // 0: 1-D bulk copies from `cols` pointers
@@ -27,6 +41,13 @@ struct FastParams {
   uint32_t scale_offset;             // fp8 mode: byte offset of the UE8M0 scales
   uint32_t sched;                    // producer schedule: 0 loader warps, 1 cooperative
   uint32_t write_end;                // bytes [num_cols*dsz, write_end) of a row are zero-filled
+  // bytes [tail_lo, tail_hi) (16-byte multiples, tail_lo >= prefix end) are written by the
+  // tail step: zeros plus the tail fields that live there; empty when tail_hi <= tail_lo
+  uint32_t tail_lo;
+  uint32_t tail_hi;
+  uint32_t num_tail;
+  uint32_t pad_;
+  TailField tail[RSDL_MAX_TAIL_FIELDS];
   uint8_t* dst[RSDL_MAX_TRAINERS];   // epoch-slot base per trainer (local/peer)
 };
 

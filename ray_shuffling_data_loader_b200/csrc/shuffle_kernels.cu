@@ -198,6 +198,52 @@ dest_pointer(unsigned long long gi, const PermKeyDev& key, const PlanDev& plan,
   return reinterpret_cast<unsigned long long>(dst[trainer]) + slot * row_pitch;
 }
 
+// Value of a tail field for chunk-local source row `row`, as the low 4 or 8 bytes of
+// the result. Deliberately a short list - bit copies of 4- and 8-byte types and the three
+// 8 -> 4 byte conversions of mode 4 (same rounding: RNE / truncation) - so that the
+// non-inlined tail_step stays small; anything else remains with the generic kernel.
+__device__ __forceinline__ unsigned long long tail_value(const TailField& f, unsigned long long row) {
+  if (rsdl_itemsize(f.src_code) == 4)
+    return *reinterpret_cast<const uint32_t*>(f.src + row * 4ull);
+  const unsigned long long v = *reinterpret_cast<const unsigned long long*>(f.src + row * 8ull);
+  if (f.dst_code == f.src_code) return v;
+  if (f.dst_code == DT_I32) return static_cast<uint32_t>(v);                       // int64 -> int32
+  if (f.src_code == DT_F64)                                                          // float64 -> f32
+    return __float_as_uint(__double2float_rn(__longlong_as_double(static_cast<long long>(v))));
+  return __float_as_uint(__ll2float_rn(static_cast<long long>(v)));                 // int64 -> f32
+}
+
+// Bytes [tail_lo, tail_hi) of 4 consecutive rows (destinations d0..d3, 0 = skip; chunk-
+// local source rows row0..row0+3): zeros plus the small fields that follow the prefix,
+// loaded straight from their source columns. Lane q of the row group writes the 16-byte
+// groups q, q+8, ... - every row's tail is again whole 16-byte stores.
+__device__ __noinline__ void tail_step(const FastParams* p, unsigned long long d0,
+                                       unsigned long long d1, unsigned long long d2,
+                                       unsigned long long d3, unsigned long long row0, int q) {
+  const uint32_t ngroups = (p->tail_hi - p->tail_lo) >> 4;
+  for (uint32_t tg = q; tg < ngroups; tg += 8) {
+    const uint32_t off = p->tail_lo + (tg << 4);
+    for (int j = 0; j < 4; ++j) {
+      const unsigned long long d = j == 0 ? d0 : (j == 1 ? d1 : (j == 2 ? d2 : d3));
+      if (!d) continue;
+      uint32_t w0 = 0u, w1 = 0u, w2 = 0u, w3 = 0u;
+      for (uint32_t t = 0; t < p->num_tail; ++t) {
+        const uint32_t doff = p->tail[t].dst_off;
+        if (doff < off || doff >= off + 16u) continue;
+        const unsigned long long bits = tail_value(p->tail[t], row0 + j);
+        const uint32_t lo = static_cast<uint32_t>(bits), hi = static_cast<uint32_t>(bits >> 32);
+        const uint32_t wi = (doff - off) >> 2;
+        const bool wide = rsdl_itemsize(p->tail[t].dst_code) == 8;
+        if (wi == 0) { w0 = lo; if (wide) w1 = hi; }
+        else if (wi == 1) { w1 = lo; }
+        else if (wi == 2) { w2 = lo; if (wide) w3 = hi; }
+        else { w3 = lo; }
+      }
+      stg128(reinterpret_cast<void*>(d + off), w0, w1, w2, w3);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // K2 shuffle_scatter, fast path: uniform 4-byte source columns
 // ---------------------------------------------------------------------------
@@ -264,7 +310,12 @@ struct alignas(1024) FastSmem {
   uint64_t turn[kIndexWarps];  // token ring: index warps publish tiles in order
 };
 
-template <int MODE>
+// TAIL = the row has tail fields / a tail range (FastParams::tail_*): a separate
+// instantiation, because the call to tail_step costs the kernel ~25 registers per thread
+// and the tail-less kernels (the headline f32 / bf16 tables) must keep their footprint -
+// what is left of the register file decides how many CTAs of the trainer's kernels can
+// run next to the persistent scatter CTA.
+template <int MODE, bool TAIL = false>
 __global__ void __launch_bounds__(kThreadsFor<MODE>, ModeTraits<MODE>::MIN_CTAS)
 scatter_tma_kernel(const __grid_constant__ FastParams p) {
   using T = ModeTraits<MODE>;
@@ -690,6 +741,14 @@ scatter_tma_kernel(const __grid_constant__ FastParams p) {
           }
         }
         }  // SRC == 4
+        // ---- tail step: bytes [tail_lo, tail_hi) of every row (see tail_step) - once per
+        // tile, with the last column panel; a real call, so that its registers (type
+        // dispatch, fp64 conversions) do not count against the main loop's
+        if constexpr (TAIL) {
+          if (panel + 1 == p.num_panels)
+            tail_step(&p, d[0], d[1], d[2], d[3],
+                      tile * static_cast<unsigned long long>(kTileRows) + rg * 4, q);
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.empty[stage]);
@@ -1119,18 +1178,24 @@ __global__ void wait_flags_kernel(const uint32_t* flags, uint32_t count, uint32_
 // ---------------------------------------------------------------------------
 // Host launchers
 // ---------------------------------------------------------------------------
-template <int MODE>
-static void launch_fast_mode(const FastParams& p, int grid, cudaStream_t stream) {
+template <int MODE, bool TAIL>
+static void launch_fast_variant(const FastParams& p, int grid, cudaStream_t stream) {
   const size_t smem = sizeof(FastSmem<MODE>) + 1024;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(scatter_tma_kernel<MODE>,
+    cudaError_t e = cudaFuncSetAttribute(scatter_tma_kernel<MODE, TAIL>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     configured = true;
   }
-  scatter_tma_kernel<MODE><<<grid, kThreadsFor<MODE>, smem, stream>>>(p);
+  scatter_tma_kernel<MODE, TAIL><<<grid, kThreadsFor<MODE>, smem, stream>>>(p);
+}
+
+template <int MODE>
+static void launch_fast_mode(const FastParams& p, int grid, cudaStream_t stream) {
+  if (p.tail_hi > p.tail_lo) launch_fast_variant<MODE, true>(p, grid, stream);
+  else launch_fast_variant<MODE, false>(p, grid, stream);
 }
 
 #define RSDL_MODE_SWITCH(mode, EXPR)                     \

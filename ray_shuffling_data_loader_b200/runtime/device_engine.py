@@ -135,7 +135,7 @@ class DeviceShuffleEngine:
                  backpressure: Optional[str] = None, numa_bind: Optional[bool] = None,
                  tmap_mode: Optional[int] = None, sched: Optional[int] = None,
                  exchange_group=None, chunk_passes: Optional[int] = None,
-                 shuffle_priority: str = "low"):
+                 shuffle_priority: str = "low", tail_fields: bool = True):
         import torch
         self.C = load_native()
         self.torch = torch
@@ -188,6 +188,7 @@ class DeviceShuffleEngine:
         self.resident, self.exchange, self.wait_mode = resident, exchange, wait_mode
         self.flag_timeout_s = flag_timeout_s
         self.force_generic = force_generic
+        self.fold_tail_fields = bool(tail_fields)     # False: trailing scalars go to the generic kernel
         self.use_tensor_map = use_tensor_map
         # Slot reuse gate (the device analogue of the queue actor's epoch window,
         # reference batch_queue.py:406-418): "stream" enqueues a wait kernel on
@@ -469,6 +470,19 @@ class DeviceShuffleEngine:
                 self.fast_mode = mode
                 self.fast_field_idx = list(range(nfast))
         rest = list(range(nfast, len(fields)))
+        # Tail fields: a few small scalars behind the prefix (a float32 label behind fp8 /
+        # bf16 / int64 features, an id behind float features) are folded into the fast
+        # kernel's stores instead of costing a second kernel and one more sub-sector write
+        # transaction per row (csrc/kernels.h::TailField).
+        self.tail_field_idx: List[int] = []
+        self.tail_range = (0, 0)
+        if nfast and rest and getattr(self, "fold_tail_fields", True) \
+                and self._tails_eligible(rest, fast_ranges[0][1]):
+            self.tail_field_idx = rest
+            hi = lay.scale_offset if self.fast_mode == 2 else lay.row_pitch
+            self.tail_range = (fast_ranges[0][1], hi)
+            fast_ranges = [(0, hi)] + list(fast_ranges[1:])
+            rest = []
         if not self.force_generic:
             self.wide_field_idx = [i for i in rest if fields[i].width >= self._WIDE_MIN]
         generic = [i for i in rest if i not in self.wide_field_idx]
@@ -498,6 +512,29 @@ class DeviceShuffleEngine:
                                      "reorder feature columns so same-typed scalars are adjacent")
         self.generic_runs = runs
         self.generic_field_idx = [i for r in runs for i in r[0]]
+
+    def _tails_eligible(self, idxs: List[int], fast_end: int) -> bool:
+        """May the fields ``idxs`` (everything behind the fast prefix) ride the fast
+        kernel as tail fields? At most 4 scalars, 4- or 8-byte destinations, only bit
+        copies and the three 8 -> 4 byte conversions, inside [fast_end, pitch) - and, with
+        the fp8 scale bytes, in front of them."""
+        lay, fields = self.layout, self.src_fields
+        if len(idxs) > self.C_MAX_TAIL or fast_end % 16:
+            return False
+        hi = lay.scale_offset if self.fast_mode == 2 else lay.row_pitch
+        for i in idxs:
+            f = fields[i]
+            ssz, dsz = L.itemsize(f.src_code), L.itemsize(f.dst_code)
+            if f.width != 1 or dsz not in (4, 8) or ssz not in (4, 8):
+                return False
+            same = f.dst_code == f.src_code
+            if not (same or (ssz == 8 and (f.src_code, f.dst_code) in _KINDS_8_TO_4)):
+                return False
+            if f.offset < fast_end or f.offset + dsz > hi or f.offset % dsz:
+                return False
+        return True
+
+    C_MAX_TAIL = 4      # RSDL_MAX_TAIL_FIELDS (csrc/kernels.h)
 
     def _fast_prefix(self):
         """(number of leading fields the TMA kernel takes, byte ranges it writes,
@@ -777,7 +814,11 @@ class DeviceShuffleEngine:
                            tmap_mode=self.tmap_mode,
                            kinds=self.fast_kinds_dev if self.fast_mode == 4 else 0,
                            write_end=self.fast_write_end,
-                           sched=self.sched, slot_lo=slot_lo, slot_hi=slot_hi)
+                           sched=self.sched, slot_lo=slot_lo, slot_hi=slot_hi,
+                           tail=[(ptrs[i], self.src_fields[i].src_code,
+                                  self.src_fields[i].dst_code, self.src_fields[i].offset)
+                                 for i in self.tail_field_idx],
+                           tail_lo=self.tail_range[0], tail_hi=self.tail_range[1])
             self.launches += 1
             self.scatter_launches += 1
         for i in self.wide_field_idx:

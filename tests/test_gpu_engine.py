@@ -115,15 +115,19 @@ def test_fast_fp8_block_scaled_matches_golden(tmp_path_factory, ncols):
         dev.close(); cpu.close()
 
 
-def test_split_fast_features_generic_label(tmp_path_factory):
-    files = _float_files(tmp_path_factory, 65, name="s")
+@pytest.mark.parametrize("tails", [True, False])
+def test_split_fast_features_generic_label(tmp_path_factory, tails):
+    """bf16 features + a float32 label + an int64 key: the two trailing scalars ride the
+    fast kernel as tail fields (one launch), or - tail_fields=False - the generic kernel."""
+    files = _float_files(tmp_path_factory, 65, name=f"s{int(tails)}")
     feats = [f"f{i}" for i in range(64)]
 
     def fn(schema):
         return L.build_layout([(c, L.DT_F32, L.DT_BF16, 1) for c in feats]
                               + [("labels", L.DT_F32, L.DT_F32, 1), ("key", L.DT_I64, L.DT_I64, 1)])
-    cpu, dev = _engines(files, fn, 2)
-    assert dev.fast_mode == 1 and len(dev.generic_field_idx) == 2
+    cpu, dev = _engines(files, fn, 2, tail_fields=tails)
+    assert dev.fast_mode == 1
+    assert (len(dev.tail_field_idx), len(dev.generic_field_idx)) == ((2, 0) if tails else (0, 2))
     try:
         _compare_epochs(cpu, dev, epochs=(0, 1))
     finally:
@@ -188,24 +192,27 @@ def test_typed64_convert_matches_golden(tmp_path_factory, ncols, trainers):
         dev.close(); cpu.close()
 
 
-def test_typed64_prefix_then_generic_tail(small_dataset):
-    """The torch default on DATA_SPEC plus an int64 key kept as int64: the
-    float32 prefix rides mode 4, the 8-byte key the generic kernel."""
+@pytest.mark.parametrize("tails,passes", [(True, 1), (True, 3), (False, 1)])
+def test_typed64_prefix_then_generic_tail(small_dataset, tails, passes):
+    """The torch default on DATA_SPEC plus an int64 key kept as int64: the float32
+    prefix rides mode 4, the 8-byte key is a tail field (or the generic kernel's)."""
     files, n = small_dataset
 
     def fn(schema):
         feats = [c for c in schema if c not in ("key",)]
         return L.build_layout([(c, schema[c][0], L.DT_F32, 1) for c in feats]
                               + [("key", L.DT_I64, L.DT_I64, 1)])
-    cpu, dev = _engines(files, fn, 2)
-    assert dev.fast_mode == 4 and len(dev.generic_field_idx) == 1
+    cpu, dev = _engines(files, fn, 2, tail_fields=tails, chunk_passes=passes)
+    assert dev.fast_mode == 4
+    assert (len(dev.tail_field_idx), len(dev.generic_field_idx)) == ((1, 0) if tails else (0, 1))
     try:
         _compare_epochs(cpu, dev, epochs=(0, 1))
     finally:
         dev.close(); cpu.close()
 
 
-def test_prefix_trimmed_to_whole_16_byte_groups(small_dataset):
+@pytest.mark.parametrize("tails,resident", [(True, "hbm"), (True, "host"), (False, "hbm")])
+def test_prefix_trimmed_to_whole_16_byte_groups(small_dataset, tails, resident):
     """5 x (int64 -> f32) followed by an int64 at byte 24: the TMA kernel takes
     the 4 fields of the full 16-byte group, the generic kernel the rest."""
     files, n = small_dataset
@@ -213,9 +220,13 @@ def test_prefix_trimmed_to_whole_16_byte_groups(small_dataset):
     def fn(schema):
         return L.build_layout([(f"embeddings_name{i}", L.DT_I64, L.DT_F32, 1) for i in range(5)]
                               + [("key", L.DT_I64, L.DT_I64, 1), ("labels", L.DT_F64, L.DT_F32, 1)])
-    cpu, dev = _engines(files, fn, 2)
+    opts = dict(tail_fields=tails, resident=resident)
+    if resident == "host":
+        opts["stream_chunk_rows"] = 1024
+    cpu, dev = _engines(files, fn, 2, **opts)
     assert dev.fast_mode == 4 and len(dev.fast_field_idx) == 4 and dev.fast_write_end == 16
-    assert len(dev.generic_field_idx) == 3
+    # embeddings_name4 (int64 -> f32), key (int64) and labels (float64 -> f32) follow
+    assert (len(dev.tail_field_idx), len(dev.generic_field_idx)) == ((3, 0) if tails else (0, 3))
     try:
         _compare_epochs(cpu, dev, epochs=(0, 1))
     finally:
@@ -587,3 +598,21 @@ def test_destination_offsets_beyond_4_gib():
     # every row written exactly once: the column-0 sums agree
     assert torch.allclose(dst.view(torch.float32)[:, 0].sum(dtype=torch.float64),
                           src[0, :n].sum(dtype=torch.float64), rtol=1e-9)
+
+
+def test_fp8_features_with_f32_label_and_key_as_tail_fields(tmp_path_factory):
+    """Block-scaled fp8 features, a float32 label and an int64 key between the payload and
+    the UE8M0 scale bytes: one launch of the fast kernel writes all of it."""
+    files = _float_files(tmp_path_factory, 65, name="fp8tail")
+    feats = [f"f{i}" for i in range(64)]
+
+    def fn(schema):
+        return L.build_layout([(c, L.DT_F32, L.DT_FP8, 1) for c in feats]
+                              + [("labels", L.DT_F32, L.DT_F32, 1)], fp8_block_scale=True)
+    cpu, dev = _engines(files, fn, 2)
+    assert dev.fast_mode == 2 and len(dev.tail_field_idx) == 1 and not dev.generic_runs
+    assert dev.tail_range == (64, dev.layout.scale_offset)
+    try:
+        _compare_epochs(cpu, dev, epochs=(0, 1, 2))
+    finally:
+        dev.close(); cpu.close()

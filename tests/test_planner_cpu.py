@@ -22,6 +22,9 @@ def _cover(eng):
     ranges = []
     if eng.fast_mode >= 0:
         ranges.append((0, eng.fast_write_end))
+        if eng.tail_range[1] > eng.tail_range[0]:
+            assert eng.tail_range[0] >= eng.fast_write_end      # tail step starts behind the prefix
+            ranges.append(eng.tail_range)
     for i in eng.wide_field_idx:
         f = eng.src_fields[i]
         ranges.append((f.offset, f.offset + f.dst_bytes))
@@ -137,8 +140,14 @@ def test_planner_invariants_property():
         except ValueError as e:           # the documented refusal, never a wrong plan
             assert "overlap" in str(e)
             return
-        claimed = sorted(eng.fast_field_idx + eng.wide_field_idx + eng.generic_field_idx)
+        claimed = sorted(eng.fast_field_idx + eng.tail_field_idx + eng.wide_field_idx
+                         + eng.generic_field_idx)
         assert claimed == list(range(len(lay.fields)))
+        for i in eng.tail_field_idx:                 # tails: small scalars inside the tail range
+            f = lay.fields[i]
+            assert f.width == 1 and L.itemsize(f.dst_code) in (4, 8)
+            assert eng.tail_range[0] <= f.offset and f.offset + f.dst_bytes <= eng.tail_range[1]
+        assert len(eng.tail_field_idx) <= 4 and not (eng.tail_field_idx and eng.generic_field_idx)
         ranges = _cover(eng)
         assert all(b <= lay.row_pitch for _, b in ranges)
         for i in eng.fast_field_idx:
@@ -168,7 +177,9 @@ def test_dataframe_layout_stores_the_tma_class_first():
     assert lay.field("key").offset == 256 and lay.row_pitch == 288
     eng = _plan(lay)
     assert eng.fast_mode == 0 and len(eng.fast_field_idx) == 64
-    assert [eng.src_fields[i].name for i in eng.generic_field_idx] == ["key"]
+    # the key rides the fast kernel as a tail field: no second (generic) launch
+    assert [eng.src_fields[i].name for i in eng.tail_field_idx] == ["key"]
+    assert not eng.generic_runs and eng.tail_range == (256, 288)
     _cover(eng)
     # natural order already optimal (DATA_SPEC + key: all 8-byte) -> untouched
     from ray_shuffling_data_loader_b200.data_generation import DATA_SPEC
