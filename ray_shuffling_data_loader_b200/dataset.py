@@ -227,15 +227,18 @@ class ShufflingDataset:
         return packed_to_dataframe(_to_numpy(packed), layout)
 
     def _frames_apply(self, chunk: ShuffledChunk) -> bool:
-        """Per-chunk DataFrames: pandas output from host (numpy) epoch buffers."""
+        """Per-chunk DataFrames: pandas output from host (numpy) epoch buffers, from
+        chunks shipped by the owning process, and - when ``output="pandas"`` is asked for
+        explicitly - from device buffers (one D2H copy per chunk instead of one per batch)."""
         if self._output not in (None, "pandas"):
             return False
         import numpy as np
         data = getattr(chunk.buffer, "data", None)
+        if self._output == "pandas":
+            return data is not None
         if not isinstance(data, np.ndarray):
             return False
-        if self._output is None:
-            self._output = "pandas"
+        self._output = "pandas"
         return True
 
     def _raise_driver_error(self):

@@ -181,3 +181,24 @@ def test_pandas_list_column_cuda(tmp_path):
         ys.append(y[:, 0])
     assert sorted(torch.cat(ys).tolist()) == list(range(n))
     ds.dataset.close()
+
+
+def test_pandas_output_from_device_buffers(small_dataset):
+    """output="pandas" on the GPU backend: one D2H copy and one native unpack per reducer
+    chunk, batches are slices of the chunk frames - same DataFrames as the CPU backend."""
+    import pandas as pd
+    files, n = small_dataset
+    g = ShufflingDataset(files, 2, 1, 777, 0, num_reducers=3, seed=5, output="pandas",
+                         queue_name="gpd-a")
+    c = ShufflingDataset(files, 2, 1, 777, 0, num_reducers=3, seed=5, backend="cpu",
+                         queue_name="gpd-b")
+    assert g.engine.device == "cuda"
+    for epoch in range(2):
+        g.set_epoch(epoch); c.set_epoch(epoch)
+        rows = 0
+        for gb, cb in zip(g, c):
+            assert isinstance(gb, pd.DataFrame) and list(gb.columns) == list(cb.columns)
+            pd.testing.assert_frame_equal(gb.reset_index(drop=True), cb.reset_index(drop=True))
+            rows += len(gb)
+        assert rows == n
+    g.close(); c.close()
