@@ -206,49 +206,62 @@ dest_pointer(unsigned long long gi, const PermKeyDev& key, const PlanDev& plan,
   return reinterpret_cast<unsigned long long>(dst[trainer]) + slot * row_pitch;
 }
 
-// Value of a tail field for chunk-local source row `row`, as the low 4 or 8 bytes of
-// the result. Deliberately a short list - bit copies of 4- and 8-byte types and the three
-// 8 -> 4 byte conversions of mode 4 (same rounding: RNE / truncation) - so that the
+// Destination bits (low 4 or 8 bytes) of a tail field whose raw source value is `raw`.
+// Deliberately a short list - bit copies of 4- and 8-byte types and the three 8 -> 4
+// byte conversions of mode 4 (same rounding: RNE / truncation) - so that the
 // non-inlined tail_step stays small; anything else remains with the generic kernel.
-__device__ __forceinline__ unsigned long long tail_value(const TailField& f, unsigned long long row) {
-  if (rsdl_itemsize(f.src_code) == 4)
-    return *reinterpret_cast<const uint32_t*>(f.src + row * 4ull);
-  const unsigned long long v = *reinterpret_cast<const unsigned long long*>(f.src + row * 8ull);
-  if (f.dst_code == f.src_code) return v;
-  if (f.dst_code == DT_I32) return static_cast<uint32_t>(v);                       // int64 -> int32
+__device__ __forceinline__ unsigned long long tail_convert(const TailField& f, unsigned long long raw) {
+  if (f.dst_code == f.src_code) return raw;
+  if (f.dst_code == DT_I32) return static_cast<uint32_t>(raw);                       // int64 -> int32
   if (f.src_code == DT_F64)                                                          // float64 -> f32
-    return __float_as_uint(__double2float_rn(__longlong_as_double(static_cast<long long>(v))));
-  return __float_as_uint(__ll2float_rn(static_cast<long long>(v)));                 // int64 -> f32
+    return __float_as_uint(__double2float_rn(__longlong_as_double(static_cast<long long>(raw))));
+  return __float_as_uint(__ll2float_rn(static_cast<long long>(raw)));               // int64 -> f32
 }
 
 // Bytes [tail_lo, tail_hi) of 4 consecutive rows (destinations d0..d3, 0 = skip; chunk-
-// local source rows row0..row0+3): zeros plus the small fields that follow the prefix,
-// loaded straight from their source columns. Lane q of the row group writes the 16-byte
-// groups q, q+8, ... - every row's tail is again whole 16-byte stores.
+// local source rows row0..row0+3, row0 % 4 == 0): zeros plus the small fields that
+// follow the prefix. Lane q of the row group writes the 16-byte groups q, q+8, ... - every
+// row's tail is again whole 16-byte stores. A field's values for the 4 rows are one
+// 16-byte (4-byte sources) or two 16-byte (8-byte sources) vector loads from its source
+// column (columns are padded to whole tiles, so rows past the end are readable).
 __device__ __noinline__ void tail_step(const FastParams* p, unsigned long long d0,
                                        unsigned long long d1, unsigned long long d2,
                                        unsigned long long d3, unsigned long long row0, int q) {
   const uint32_t ngroups = (p->tail_hi - p->tail_lo) >> 4;
   for (uint32_t tg = q; tg < ngroups; tg += 8) {
     const uint32_t off = p->tail_lo + (tg << 4);
-    for (int j = 0; j < 4; ++j) {
-      const unsigned long long d = j == 0 ? d0 : (j == 1 ? d1 : (j == 2 ? d2 : d3));
-      if (!d) continue;
-      uint32_t w0 = 0u, w1 = 0u, w2 = 0u, w3 = 0u;
-      for (uint32_t t = 0; t < p->num_tail; ++t) {
-        const uint32_t doff = p->tail[t].dst_off;
-        if (doff < off || doff >= off + 16u) continue;
-        const unsigned long long bits = tail_value(p->tail[t], row0 + j);
-        const uint32_t lo = static_cast<uint32_t>(bits), hi = static_cast<uint32_t>(bits >> 32);
-        const uint32_t wi = (doff - off) >> 2;
-        const bool wide = rsdl_itemsize(p->tail[t].dst_code) == 8;
-        if (wi == 0) { w0 = lo; if (wide) w1 = hi; }
-        else if (wi == 1) { w1 = lo; }
-        else if (wi == 2) { w2 = lo; if (wide) w3 = hi; }
-        else { w3 = lo; }
+    uint32_t w[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[j][0] = w[j][1] = w[j][2] = w[j][3] = 0u;
+    for (uint32_t t = 0; t < p->num_tail; ++t) {
+      const uint32_t doff = p->tail[t].dst_off;
+      if (doff < off || doff >= off + 16u) continue;
+      unsigned long long raw[4];
+      if (rsdl_itemsize(p->tail[t].src_code) == 4) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p->tail[t].src + row0 * 4ull));
+        raw[0] = v.x; raw[1] = v.y; raw[2] = v.z; raw[3] = v.w;
+      } else {
+        const ulonglong2* s2 = reinterpret_cast<const ulonglong2*>(p->tail[t].src + row0 * 8ull);
+        const ulonglong2 a = __ldg(s2), b = __ldg(s2 + 1);
+        raw[0] = a.x; raw[1] = a.y; raw[2] = b.x; raw[3] = b.y;
       }
-      stg128(reinterpret_cast<void*>(d + off), w0, w1, w2, w3);
+      const uint32_t wi = (doff - off) >> 2;
+      const bool wide = rsdl_itemsize(p->tail[t].dst_code) == 8;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const unsigned long long bits = rsdl_itemsize(p->tail[t].src_code) == 4
+            ? raw[j] : tail_convert(p->tail[t], raw[j]);
+        const uint32_t lo = static_cast<uint32_t>(bits), hi = static_cast<uint32_t>(bits >> 32);
+        if (wi == 0) { w[j][0] = lo; if (wide) w[j][1] = hi; }
+        else if (wi == 1) { w[j][1] = lo; }
+        else if (wi == 2) { w[j][2] = lo; if (wide) w[j][3] = hi; }
+        else { w[j][3] = lo; }
+      }
     }
+    if (d0) stg128(reinterpret_cast<void*>(d0 + off), w[0][0], w[0][1], w[0][2], w[0][3]);
+    if (d1) stg128(reinterpret_cast<void*>(d1 + off), w[1][0], w[1][1], w[1][2], w[1][3]);
+    if (d2) stg128(reinterpret_cast<void*>(d2 + off), w[2][0], w[2][1], w[2][2], w[2][3]);
+    if (d3) stg128(reinterpret_cast<void*>(d3 + off), w[3][0], w[3][1], w[3][2], w[3][3]);
   }
 }
 
